@@ -1,0 +1,79 @@
+// Parametric piecewise dB-per-octave lowpass, device side.
+//
+// Restates the semantics of design_filter (utils/blind_bwe_utils.py:82-119 of
+// eloimoliner/BABE) without the sequential masked overwrites: bin k is owned by
+// the LAST breakpoint i whose first bin kf[i] (first k with f[k] >= fc[i]) is
+// <= k, and the gain of segment i is anchored at the value its predecessor
+// took at bin kf[i].  The fp32 operation order of the reference
+// (A*log2(f/fc) -> /20 -> 10** -> *anchor) is kept.
+#pragma once
+#include "common.cuh"
+
+namespace babe {
+
+struct FilterSegs {
+  int K;
+  int kf[BABE_MAX_BREAKPOINTS];       // first bin >= fc[i] (F if none)
+  int parent[BABE_MAX_BREAKPOINTS];   // owner of bin kf[i] before segment i is written (-1: H=1)
+  float fc[BABE_MAX_BREAKPOINTS];
+  float A[BABE_MAX_BREAKPOINTS];
+  float anchor[BABE_MAX_BREAKPOINTS]; // multiplicative anchor of segment i
+  int bad;                            // some fc[i>=1] above the last bin (reference: IndexError)
+};
+
+__device__ __forceinline__ float seg_gain(float A, float fc, float f) {
+  // 10 ** (A * log2(f / fc) / 20)
+  const float t = __fdiv_rn(__fmul_rn(A, log2f(__fdiv_rn(f, fc))), 20.0f);
+  return exp10f(t);
+}
+
+__device__ __forceinline__ int first_bin_ge(const float* f, int F, float v) {
+  // f is non-decreasing; NaN v -> F
+  int lo = 0, hi = F;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (f[mid] >= v) hi = mid; else lo = mid + 1;
+  }
+  return (v == v) ? lo : F;
+}
+
+// Executed by ONE thread.  f may live in shared or global memory.
+__device__ inline void build_segments(FilterSegs& s, const float* fc, const float* A, int K,
+                                      const float* f, int F) {
+  s.K = K;
+  s.bad = 0;
+  for (int i = 0; i < K; ++i) {
+    s.fc[i] = fc[i];
+    s.A[i] = A[i];
+    s.kf[i] = first_bin_ge(f, F, s.fc[i]);
+  }
+  for (int i = 0; i < K; ++i) {
+    int p = -1;
+    for (int j = 0; j < i; ++j)
+      if (s.kf[j] <= s.kf[i]) p = j;
+    s.parent[i] = p;
+    if (i > 0 && s.kf[i] >= F) { s.bad = 1; s.anchor[i] = 1.0f; continue; }
+    if (i == 0 || p < 0) {
+      s.anchor[i] = 1.0f;
+    } else {
+      s.anchor[i] = __fmul_rn(seg_gain(s.A[p], s.fc[p], f[s.kf[i]]), s.anchor[p]);
+    }
+  }
+}
+
+__device__ __forceinline__ int bin_owner(const FilterSegs& s, int k) {
+  int o = -1;
+#pragma unroll 4
+  for (int i = 0; i < s.K; ++i)
+    if (s.kf[i] <= k) o = i;
+  return o;
+}
+
+__device__ __forceinline__ float bin_gain(const FilterSegs& s, int k, float fk) {
+  const int o = bin_owner(s, k);
+  if (o < 0) return 1.0f;
+  const float g = seg_gain(s.A[o], s.fc[o], fk);
+  return (o == 0) ? g : __fmul_rn(g, s.anchor[o]);
+}
+
+}  // namespace babe

@@ -1,0 +1,310 @@
+// Filter design, its vector-Jacobian product, the device-resident projected
+// gradient descent on (fc, A), and spectrogram-domain magnitude statistics.
+//
+// Reference semantics: design_filter (utils/blind_bwe_utils.py:82-119),
+// apply_filter_and_norm_STFTmag_fweighted (:250-296) and
+// BlindSampler.fit_params (testing/blind_bwe_sampler.py:533-595) of
+// eloimoliner/BABE; analytic gradients per SURVEY Appendix A.2 / A.3.
+#include <math.h>
+
+#include "common.cuh"
+#include "filter_design.cuh"
+
+namespace babe {
+
+constexpr int KMAX = BABE_MAX_BREAKPOINTS;
+constexpr int FIT_THREADS = 512;
+constexpr int FIT_WARPS = FIT_THREADS / 32;
+
+// ---------------------------------------------------------------------------
+__global__ void k_design_filter(const float* fc, const float* A, int K, const float* gain_db,
+                                const float* freqs, int F, float* H, int* status) {
+  __shared__ FilterSegs segs;
+  if (threadIdx.x == 0) {
+    build_segments(segs, fc, A, K, freqs, F);
+    if (segs.bad && status != nullptr && blockIdx.x == 0) *status = 1;
+  }
+  __syncthreads();
+  float g = 1.0f;
+  if (gain_db != nullptr) g = exp10f(__fdiv_rn(gain_db[0], 20.0f));
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < F; k += gridDim.x * blockDim.x) {
+    float h = bin_gain(segs, k, freqs[k]);
+    if (gain_db != nullptr) h = __fmul_rn(h, g);
+    H[k] = h;
+  }
+}
+
+// Block-wide sum of NV doubles held per thread (v[0..NV)), result valid in
+// thread 0 (returned in v).  scratch: FIT_WARPS * NV doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) scratch[warp * NV + i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = 0.0;
+      for (int w = 0; w < FIT_WARPS; ++w) s += scratch[w * NV + i];
+      v[i] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// Accumulate, for the calling thread's bins, per-segment sums
+//   s[i] += u_k                (k owned by i)
+//   l[i] += u_k log2(f_k/fc_i) (k owned by i)
+// where u_k = dL/dH_k * H_k.
+// Then (thread 0) the chain rule through the anchors gives dL/dfc, dL/dA.
+__device__ __forceinline__ void finish_param_grads(const FilterSegs& sg, const float* f, int F,
+                                                   const double* s, const double* l,
+                                                   double* gfc, double* gA) {
+  const double alpha = 0.11512925464970229;   // ln(10)/20
+  const double ln2 = 0.6931471805599453;
+  for (int i = 0; i < sg.K; ++i) { gfc[i] = 0.0; gA[i] = 0.0; }
+  for (int i = 0; i < sg.K; ++i) {
+    if (sg.kf[i] >= F) continue;                 // owns no bin, s[i] = l[i] = 0
+    gA[i] += alpha * l[i];
+    gfc[i] += -alpha * (double)sg.A[i] / ((double)sg.fc[i] * ln2) * s[i];
+    int c = i;
+    while (sg.parent[c] >= 0) {
+      const int j = sg.parent[c];
+      gA[j] += alpha * (double)log2f(__fdiv_rn(f[sg.kf[c]], sg.fc[j])) * s[i];
+      gfc[j] += -alpha * (double)sg.A[j] / ((double)sg.fc[j] * ln2) * s[i];
+      c = j;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FIT_THREADS, 1)
+k_design_filter_vjp(const float* fc, const float* A, int K, const float* gain_db,
+                    const float* freqs, int F, const float* gH, float* gfc_out, float* gA_out,
+                    float* ggain_out) {
+  __shared__ FilterSegs segs;
+  __shared__ double scratch[FIT_WARPS * (2 * KMAX + 1)];
+  if (threadIdx.x == 0) build_segments(segs, fc, A, K, freqs, F);
+  __syncthreads();
+  float g = 1.0f;
+  if (gain_db != nullptr) g = exp10f(__fdiv_rn(gain_db[0], 20.0f));
+  double v[2 * KMAX + 1];
+#pragma unroll
+  for (int i = 0; i < 2 * KMAX + 1; ++i) v[i] = 0.0;
+  for (int k = threadIdx.x; k < F; k += blockDim.x) {
+    const float fk = freqs[k];
+    const int o = bin_owner(segs, k);
+    const float h = bin_gain(segs, k, fk) * g;
+    const double u = (double)gH[k] * (double)h;
+    v[2 * KMAX] += u;                              // for dL/dG
+    if (o >= 0) {
+      const double lg = (double)log2f(__fdiv_rn(fk, segs.fc[o]));
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i) {
+        if (i == o) { v[i] += u; v[KMAX + i] += u * lg; }
+      }
+    }
+  }
+  block_sum<2 * KMAX + 1>(v, scratch);
+  if (threadIdx.x == 0) {
+    double gfc[KMAX], gA[KMAX];
+    finish_param_grads(segs, freqs, F, v, v + KMAX, gfc, gA);
+    for (int i = 0; i < K; ++i) { gfc_out[i] = (float)gfc[i]; gA_out[i] = (float)gA[i]; }
+    if (ggain_out != nullptr) ggain_out[0] = (float)(0.11512925464970229 * v[2 * KMAX]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// device-resident fit loop (single CTA)
+// ---------------------------------------------------------------------------
+struct FitArgs {
+  const double* abc; const float* w; const float* freqs; int F;
+  float* params; int K; babe_fit_config cfg; int* iters_out;
+};
+
+__global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sa = reinterpret_cast<double*>(smem_raw);            // w^2 a
+  double* sb = sa + a.F;                                       // w^2 b
+  float* sf = reinterpret_cast<float*>(sb + a.F);              // freqs
+  __shared__ FilterSegs segs;
+  __shared__ double scratch[FIT_WARPS * (2 * KMAX + 1)];
+  __shared__ float cur[2 * KMAX], prev[2 * KMAX];
+  __shared__ int stop_flag;
+  __shared__ double c_total;
+
+  const int F = a.F, K = a.K;
+  {
+    double v[1] = {0.0};
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+      const double w2 = (double)a.w[k] * (double)a.w[k];
+      sa[k] = w2 * a.abc[k];
+      sb[k] = w2 * a.abc[F + k];
+      sf[k] = a.freqs[k];
+      v[0] += w2 * a.abc[2 * F + k];
+    }
+    block_sum<1>(v, scratch);
+    if (threadIdx.x == 0) {
+      c_total = v[0];
+      for (int i = 0; i < K; ++i) { cur[i] = a.params[i]; cur[KMAX + i] = a.params[K + i]; }
+      stop_flag = 0;
+    }
+  }
+  __syncthreads();
+
+  int it = 0;
+  for (int iter = 0; iter < a.cfg.max_iter; ++iter) {
+    if (threadIdx.x == 0) build_segments(segs, cur, cur + KMAX, K, sf, F);
+    __syncthreads();
+    double v[2 * KMAX + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * KMAX + 1; ++i) v[i] = 0.0;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+      const float fk = sf[k];
+      const int o = bin_owner(segs, k);
+      const double h = (double)bin_gain(segs, k, fk);
+      const double wa = sa[k], wb = sb[k];
+      v[2 * KMAX] += h * (h * wa - 2.0 * wb);            // S without the c term
+      if (o >= 0) {
+        const double u = (h * wa - wb) * h;              // (norm * dnorm/dH_k) * H_k
+        const double lg = (double)log2f(__fdiv_rn(fk, segs.fc[o]));
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i) {
+          if (i == o) { v[i] += u; v[KMAX + i] += u * lg; }
+        }
+      }
+    }
+    block_sum<2 * KMAX + 1>(v, scratch);
+    if (threadIdx.x == 0) {
+      double gfc[KMAX], gA[KMAX];
+      finish_param_grads(segs, sf, F, v, v + KMAX, gfc, gA);
+      const double S = v[2 * KMAX] + c_total;
+      const double inv_norm = 1.0 / sqrt(S > 0.0 ? S : 0.0);
+      // gradient step in fp32 like the reference (:569), then the clamps (:576-583)
+      for (int i = 0; i < K; ++i) {
+        const float g0 = (float)(gfc[i] * inv_norm), g1 = (float)(gA[i] * inv_norm);
+        cur[i] = __fsub_rn(cur[i], __fmul_rn(a.cfg.mu_fc, g0));
+        cur[KMAX + i] = __fsub_rn(cur[KMAX + i], __fmul_rn(a.cfg.mu_A, g1));
+      }
+      if (a.cfg.clamp_fc) {
+        cur[0] = fminf(fmaxf(cur[0], a.cfg.fcmin), a.cfg.fcmax);
+        for (int k = 1; k < K; ++k)
+          cur[k] = fminf(fmaxf(cur[k], __fadd_rn(cur[k - 1], 1.0f)), a.cfg.fcmax);
+      }
+      if (a.cfg.clamp_A) {
+        const float top0 = a.cfg.only_negative_A ? -1.0f : a.cfg.Amax;
+        cur[KMAX] = fminf(fmaxf(cur[KMAX], a.cfg.Amin), top0);
+        for (int k = 1; k < K; ++k) {
+          const float top = a.cfg.only_negative_A ? cur[KMAX + k - 1] : a.cfg.Amax;
+          cur[KMAX + k] = fminf(fmaxf(cur[KMAX + k], a.cfg.Amin), top);
+        }
+      }
+      if (iter > 0) {
+        float d0 = 0.f, d1 = 0.f;
+        for (int k = 0; k < K; ++k) {
+          d0 += fabsf(cur[k] - prev[k]);
+          d1 += fabsf(cur[KMAX + k] - prev[KMAX + k]);
+        }
+        if (d0 / (float)K < a.cfg.tol_fc && d1 / (float)K < a.cfg.tol_A) stop_flag = 1;
+      }
+      for (int k = 0; k < K; ++k) { prev[k] = cur[k]; prev[KMAX + k] = cur[KMAX + k]; }
+    }
+    __syncthreads();
+    it = iter + 1;
+    if (stop_flag) break;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < K; ++i) { a.params[i] = cur[i]; a.params[K + i] = cur[KMAX + i]; }
+    if (a.iters_out != nullptr) *a.iters_out = it;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// spectrogram-domain magnitude statistics: one CTA per frequency bin
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_spec_mag_stats(const float2* X, const float2* Xref,
+                                                        const float* H, const float* w, int B,
+                                                        int F, int frames, double* out) {
+  const int k = blockIdx.x;
+  const float h = H ? H[k] : 1.0f;
+  const float wk = w ? w[k] : 1.0f;
+  double sa = 0, sb = 0, sc = 0, ss = 0;
+  const long long n = (long long)B * frames;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = (int)(i / frames), m = (int)(i % frames);
+    const size_t off = ((size_t)b * F + k) * frames + m;
+    const float2 x = X[off], y = Xref[off];
+    // mirror the reference's fp32 order: sqrt(re^2+im^2), *H, *w, difference
+    const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+    const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
+    const float d = __fsub_rn(__fmul_rn(__fmul_rn(mx, h), wk), __fmul_rn(my, wk));
+    sa += (double)mx * mx; sb += (double)mx * my; sc += (double)my * my;
+    ss += (double)d * d;
+  }
+  __shared__ double red[4][4];
+  sa = warp_sum(sa); sb = warp_sum(sb); sc = warp_sum(sc); ss = warp_sum(ss);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[warp][0] = sa; red[warp][1] = sb; red[warp][2] = sc; red[warp][3] = ss; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0;
+    for (int wv = 0; wv < 4; ++wv) s += red[wv][threadIdx.x];
+    out[(size_t)threadIdx.x * F + k] = s;
+  }
+}
+
+}  // namespace babe
+
+using namespace babe;
+
+extern "C" int babe_design_filter(const float* fc, const float* A, int K, const float* gain_db,
+                                  const float* freqs, int F, float* H, int* status,
+                                  void* stream) {
+  BABE_REQUIRE(fc && A && freqs && H, BABE_EBADARG, "design_filter: null pointer");
+  BABE_REQUIRE(K >= 1 && K <= KMAX, BABE_EBADARG, "design_filter: K=%d outside [1,%d]", K, KMAX);
+  BABE_REQUIRE(F >= 1, BABE_EBADARG, "design_filter: F=%d", F);
+  const int blocks = (F + 255) / 256;
+  k_design_filter<<<blocks < 64 ? blocks : 64, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      fc, A, K, gain_db, freqs, F, H, status);
+  return check_launch("k_design_filter");
+}
+
+extern "C" int babe_design_filter_vjp(const float* fc, const float* A, int K,
+                                      const float* gain_db, const float* freqs, int F,
+                                      const float* gH, float* gfc, float* gA, float* ggain,
+                                      void* stream) {
+  BABE_REQUIRE(fc && A && freqs && gH && gfc && gA, BABE_EBADARG, "design_filter_vjp: null pointer");
+  BABE_REQUIRE(K >= 1 && K <= KMAX, BABE_EBADARG, "design_filter_vjp: K=%d outside [1,%d]", K, KMAX);
+  BABE_REQUIRE(F >= 1, BABE_EBADARG, "design_filter_vjp: F=%d", F);
+  k_design_filter_vjp<<<1, FIT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      fc, A, K, gain_db, freqs, F, gH, gfc, gA, ggain);
+  return check_launch("k_design_filter_vjp");
+}
+
+extern "C" int babe_fit_params(const double* abc, const float* w, const float* freqs, int F,
+                               float* params, int K, const babe_fit_config* cfg,
+                               int* iters_out, void* stream) {
+  BABE_REQUIRE(abc && w && freqs && params && cfg, BABE_EBADARG, "fit_params: null pointer");
+  BABE_REQUIRE(K >= 1 && K <= KMAX, BABE_EBADARG, "fit_params: K=%d outside [1,%d]", K, KMAX);
+  const size_t smem = (size_t)F * (2 * sizeof(double) + sizeof(float));
+  BABE_REQUIRE(F >= 1 && smem <= 200 * 1024, BABE_EUNSUPPORTED, "fit_params: F=%d too large", F);
+  FitArgs a{abc, w, freqs, F, params, K, *cfg, iters_out};
+  cudaFuncSetAttribute(k_fit_params, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fit_params<<<1, FIT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("k_fit_params");
+}
+
+extern "C" int babe_spec_mag_stats(const float* X, const float* Xref, const float* H,
+                                   const float* w, int B, int F, int frames, double* out,
+                                   void* stream) {
+  BABE_REQUIRE(X && Xref && out, BABE_EBADARG, "spec_mag_stats: null pointer");
+  BABE_REQUIRE(B >= 1 && F >= 1 && frames >= 1, BABE_EBADARG, "spec_mag_stats: bad shape");
+  k_spec_mag_stats<<<F, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(X), reinterpret_cast<const float2*>(Xref), H, w, B, F,
+      frames, out);
+  return check_launch("k_spec_mag_stats");
+}

@@ -1,0 +1,768 @@
+// STFT-domain operator kernels for sm_100a.
+//
+// All kernels share one transform core: a length-N complex FFT (N = R1*R2,
+// R in {16,32,64}) computed in two in-register passes by max(R1,R2) threads
+// (a "frame group"), with one shared-memory transposition between the passes.
+// Two real frames are carried through each complex transform (frame A in the
+// real part, frame B in the imaginary part).  Because the lowpass response H
+// is real and symmetric the packed spectrum can be multiplied by H directly
+// and inverted without ever separating the two frames, so the fused
+// STFT -> H -> iSTFT operator costs one forward and one inverse complex FFT
+// per PAIR of frames, the window, overlap-add and envelope division happen in
+// registers, and x is read and y written exactly once.
+//
+// Reference semantics: utils/blind_bwe_utils.py:6-39 of eloimoliner/BABE
+// (periodic Hamming window, hop N/2, right zero padding by N, center=False,
+// torch.istft envelope normalisation).
+#include <math.h>
+
+#include "common.cuh"
+#include "filter_design.cuh"
+#include "regfft.cuh"
+
+namespace babe {
+
+template <int R1_, int R2_>
+struct Geo {
+  static constexpr int R1 = R1_, R2 = R2_;
+  static constexpr int N = R1 * R2, HOP = N / 2, F = N / 2 + 1;
+  static constexpr int TPF = R1 > R2 ? R1 : R2;            // threads per frame group
+  static constexpr int EXF = R2 + 1;                        // forward exchange  [k1][n2]
+  static constexpr int EXI = R1 + 1;                        // inverse exchange  [n2][k1]
+  static constexpr int EX_ELEMS = (R1 * EXF > R2 * EXI) ? R1 * EXF : R2 * EXI;
+  static constexpr int TW_ELEMS = R1 * EXF;                 // padded twiddle table [k1][n2]
+};
+
+// ---------------------------------------------------------------------------
+// transform core
+// ---------------------------------------------------------------------------
+// in : thread t < R2 holds z[R2*n1 + t] in (ar,ai)[n1], n1 < R1
+// out: thread t < R1 holds Z[t + R1*k2] in (br,bi)[k2], k2 < R2
+template <class G>
+__device__ __forceinline__ void fwd_pair(float (&ar)[G::R1], float (&ai)[G::R1],
+                                         float (&br)[G::R2], float (&bi)[G::R2],
+                                         float2* ex, const float2* tw, int t, int bar) {
+  if (t < G::R2) {
+    fft_reg<G::R1>(ar, ai);
+#pragma unroll
+    for (int k1 = 0; k1 < G::R1; ++k1) {
+      const float2 w = tw[k1 * G::EXF + t];
+      float2 v;
+      v.x = ar[k1] * w.x - ai[k1] * w.y;
+      v.y = ar[k1] * w.y + ai[k1] * w.x;
+      ex[k1 * G::EXF + t] = v;
+    }
+  }
+  group_sync<G::TPF>(bar);
+  if (t < G::R1) {
+#pragma unroll
+    for (int n2 = 0; n2 < G::R2; ++n2) {
+      const float2 v = ex[t * G::EXF + n2];
+      br[n2] = v.x; bi[n2] = v.y;
+    }
+    fft_reg<G::R2>(br, bi);
+  }
+}
+
+// in : thread t < R1 holds Z[t + R1*k2] in (br,bi)[k2]
+// out: thread t < R2 holds N * z[R2*n1 + t] in (ar,ai)[n1]  (unnormalised)
+// The caller must have passed a group barrier since the last read of `ex`.
+template <class G>
+__device__ __forceinline__ void inv_pair(float (&br)[G::R2], float (&bi)[G::R2],
+                                         float (&ar)[G::R1], float (&ai)[G::R1],
+                                         float2* ex, const float2* tw, int t, int bar) {
+  if (t < G::R1) {
+    fft_reg<G::R2>(bi, br);   // inverse over k2 -> n2
+#pragma unroll
+    for (int n2 = 0; n2 < G::R2; ++n2) {
+      const float2 w = tw[t * G::EXF + n2];          // conj(w) below
+      float2 v;
+      v.x = br[n2] * w.x + bi[n2] * w.y;
+      v.y = bi[n2] * w.x - br[n2] * w.y;
+      ex[n2 * G::EXI + t] = v;
+    }
+  }
+  group_sync<G::TPF>(bar);
+  if (t < G::R2) {
+#pragma unroll
+    for (int k1 = 0; k1 < G::R1; ++k1) {
+      const float2 v = ex[t * G::EXI + k1];
+      ar[k1] = v.x; ai[k1] = v.y;
+    }
+    fft_reg<G::R1>(ai, ar);   // inverse over k1 -> n1
+  }
+}
+
+// Exchange so that thread t < R1 additionally sees P[k2] = Z[N - (t + R1*k2)].
+// On return (pr,pi)[k2] holds that partner value.  Needs a barrier before
+// (ex free) and leaves ex busy until the next barrier.
+template <class G>
+__device__ __forceinline__ void mirror_exchange(const float (&br)[G::R2], const float (&bi)[G::R2],
+                                                float (&pr)[G::R2], float (&pi)[G::R2],
+                                                float2* ex, int t, int bar) {
+  if (t < G::R1) {
+#pragma unroll
+    for (int k2 = 0; k2 < G::R2; ++k2) ex[t * G::EXF + k2] = make_float2(br[k2], bi[k2]);
+  }
+  group_sync<G::TPF>(bar);
+  if (t < G::R1) {
+    const int pt = (G::R1 - t) % G::R1;
+#pragma unroll
+    for (int k2 = 0; k2 < G::R2; ++k2) {
+      const int pk = (t == 0) ? ((G::R2 - k2) % G::R2) : (G::R2 - 1 - k2);
+      const float2 v = ex[pt * G::EXF + pk];
+      pr[k2] = v.x; pi[k2] = v.y;
+    }
+  }
+}
+
+// overlap-add envelope at block `blk`, offset r (< HOP) given w^2 of both halves
+__device__ __forceinline__ float ola_env(int blk, int frames, float w2lo, float w2hi) {
+  float e = 0.f;
+  if (blk >= 1 && blk - 1 < frames) e = w2hi;
+  if (blk < frames) e = __fadd_rn(e, w2lo);
+  return e;
+}
+
+// ---------------------------------------------------------------------------
+// shared-memory carve-up common to the kernels
+// ---------------------------------------------------------------------------
+template <class G>
+struct Smem {
+  float2* tw;    // TW_ELEMS
+  float* win;    // N
+  float* hs;     // F   (H/N, or bin scale)
+  float2* ex;    // groups * EX_ELEMS
+  __device__ Smem(unsigned char* base, int groups) {
+    tw = reinterpret_cast<float2*>(base);
+    ex = tw + G::TW_ELEMS;
+    win = reinterpret_cast<float*>(ex + groups * G::EX_ELEMS);
+    hs = win + G::N;
+  }
+  static size_t bytes(int groups, int extra_floats_per_group = 0) {
+    return sizeof(float2) * (G::TW_ELEMS + (size_t)groups * G::EX_ELEMS) +
+           sizeof(float) * (G::N + G::F + 3 + (size_t)groups * extra_floats_per_group);
+  }
+};
+
+template <class G>
+__device__ __forceinline__ void load_tables(Smem<G>& sm, const float* window, const float2* twiddle) {
+  for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
+    sm.win[i] = window[i];
+    const int k1 = i / G::R2, n2 = i % G::R2;
+    sm.tw[k1 * G::EXF + n2] = twiddle[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1: fused STFT -> H -> iSTFT  (forward and adjoint)
+// ---------------------------------------------------------------------------
+struct FilterArgs {
+  const float* x; float* y; int B, T;
+  const float* window; const float2* twiddle;
+  const float* H; const float* freqs; const float* fc; const float* A; int K;
+  int adjoint;
+  const float* sub; const float* row_scale; double* row_sumsq;
+  int* status;
+  int bpi;            // output blocks per work item
+  int items_per_row;  // ceil(nblk / bpi)
+  int nblk;           // output blocks that contain samples < T
+  int frames;         // 1 + T / HOP
+};
+
+template <class G, int GROUPS>
+__global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const FilterArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<G> sm(smem_raw, GROUPS);
+  __shared__ FilterSegs segs;
+
+  load_tables(sm, a.window, a.twiddle);
+  constexpr float inv_n = 1.0f / G::N;
+  if (a.H != nullptr) {
+    for (int k = threadIdx.x; k < G::F; k += blockDim.x) sm.hs[k] = a.H[k] * inv_n;
+  } else {
+    if (threadIdx.x == 0) {
+      build_segments(segs, a.fc, a.A, a.K, a.freqs, G::F);
+      if (segs.bad && a.status != nullptr && blockIdx.x == 0) *a.status = 1;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < G::F; k += blockDim.x)
+      sm.hs[k] = bin_gain(segs, k, a.freqs[k]) * inv_n;
+  }
+  __syncthreads();
+
+  const int grp = threadIdx.x / G::TPF;
+  const int t = threadIdx.x % G::TPF;
+  const int bar = 1 + grp;
+  float2* ex = sm.ex + grp * G::EX_ELEMS;
+  const long long n_items = (long long)a.B * a.items_per_row;
+
+  for (long long item = (long long)blockIdx.x * GROUPS + grp; item < n_items;
+       item += (long long)gridDim.x * GROUPS) {
+    const int row = (int)(item / a.items_per_row);
+    const int j0 = (int)(item % a.items_per_row) * a.bpi;
+    const int j1 = min(j0 + a.bpi, a.nblk);
+    const int fs = max(j0 - 1, 0);
+    const int fe = min(j1 - 1, a.frames - 1);
+    const float* xr = a.x + (size_t)row * a.T;
+    float* yr = a.y + (size_t)row * a.T;
+    const float* subr = a.sub ? a.sub + (size_t)row * a.T : nullptr;
+    const float rs = a.row_scale ? a.row_scale[row] : 1.0f;
+    float carry[G::R1 / 2];
+#pragma unroll
+    for (int i = 0; i < G::R1 / 2; ++i) carry[i] = 0.f;
+    double acc = 0.0;
+
+    for (int fA = fs; fA <= fe; fA += 2) {
+      float ar[G::R1], ai[G::R1], br[G::R2], bi[G::R2];
+      if (t < G::R2) {
+        // ---- load 3 half-frames: samples fA*HOP + R2*j + t, j < 3*R1/2
+        float xs[G::R1 + G::R1 / 2];
+        const long long base = (long long)fA * G::HOP + t;
+#pragma unroll
+        for (int j = 0; j < G::R1 + G::R1 / 2; ++j) {
+          const long long p = base + (long long)G::R2 * j;
+          float v = (p < a.T) ? __ldg(xr + p) : 0.f;
+          if (a.adjoint) {
+            const int blk = fA + j / (G::R1 / 2);
+            const int r = (j % (G::R1 / 2)) * G::R2 + t;
+            const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+            v = (p < a.T) ? __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh)) : 0.f;
+          }
+          xs[j] = v;
+        }
+        const bool hasB = (fA + 1) < a.frames;
+#pragma unroll
+        for (int n1 = 0; n1 < G::R1; ++n1) {
+          const float w = sm.win[G::R2 * n1 + t];
+          ar[n1] = xs[n1] * w;
+          ai[n1] = hasB ? xs[n1 + G::R1 / 2] * w : 0.f;
+        }
+      }
+      fwd_pair<G>(ar, ai, br, bi, ex, sm.tw, t, bar);
+      if (t < G::R1) {
+#pragma unroll
+        for (int k2 = 0; k2 < G::R2; ++k2) {
+          const int k = t + G::R1 * k2;
+          const float h = sm.hs[k <= G::N / 2 ? k : G::N - k];
+          br[k2] *= h; bi[k2] *= h;
+        }
+      }
+      group_sync<G::TPF>(bar);            // every thread has finished reading ex
+      inv_pair<G>(br, bi, ar, ai, ex, sm.tw, t, bar);
+      if (t < G::R2) {
+        // ---- window, overlap-add, normalise, store
+#pragma unroll
+        for (int n1 = 0; n1 < G::R1; ++n1) {
+          const float w = sm.win[G::R2 * n1 + t];
+          ar[n1] *= w; ai[n1] *= w;
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int blk = fA + half;
+          const bool mine = (blk >= j0) && (blk < j1);
+#pragma unroll
+          for (int n1 = 0; n1 < G::R1 / 2; ++n1) {
+            float v = half == 0 ? __fadd_rn(ar[n1], carry[n1])
+                                : __fadd_rn(ar[n1 + G::R1 / 2], ai[n1]);
+            const int r = G::R2 * n1 + t;
+            const long long p = (long long)blk * G::HOP + r;
+            if (mine && p < a.T) {
+              if (!a.adjoint) {
+                const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+                v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
+                if (subr) v -= subr[p];
+              }
+              v *= rs;
+              yr[p] = v;
+              acc += (double)v * (double)v;
+            }
+          }
+        }
+#pragma unroll
+        for (int n1 = 0; n1 < G::R1 / 2; ++n1) carry[n1] = ai[n1 + G::R1 / 2];
+      }
+      group_sync<G::TPF>(bar);            // ex free for the next pair
+    }
+    if (a.row_sumsq != nullptr) {
+      acc = warp_sum(acc);
+      if ((threadIdx.x & 31) == 0) atomicAdd(a.row_sumsq + row, acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2: STFT statistics.  z = x*w + i*y*w, one frame per transform.
+//   mode 0: a += |X|^2, b += |X||Y|, c += |Y|^2
+//   mode 1: a += Re(conj(X) G), y divided by the OLA envelope on load
+// Per-group partial sums go to workspace[group][3][F]; k_reduce_stats sums
+// them in a fixed order (deterministic).
+// ---------------------------------------------------------------------------
+struct StatsArgs {
+  const float* x; const float* y; int B, T;
+  const float* window; const float2* twiddle;
+  int mode; int frames; int fpi; int items_per_row;
+  float* partial;
+};
+
+template <class G, int GROUPS>
+__global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft_stats(const StatsArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<G> sm(smem_raw, GROUPS);
+  float* accbase = sm.hs + G::F + 3;
+  load_tables(sm, a.window, a.twiddle);
+  const int grp = threadIdx.x / G::TPF;
+  const int t = threadIdx.x % G::TPF;
+  const int bar = 1 + grp;
+  float2* ex = sm.ex + grp * G::EX_ELEMS;
+  float* acc = accbase + (size_t)grp * 3 * G::F;
+  for (int i = t; i < 3 * G::F; i += G::TPF) acc[i] = 0.f;
+  __syncthreads();
+
+  const long long n_items = (long long)a.B * a.items_per_row;
+  for (long long item = (long long)blockIdx.x * GROUPS + grp; item < n_items;
+       item += (long long)gridDim.x * GROUPS) {
+    const int row = (int)(item / a.items_per_row);
+    const int f0 = (int)(item % a.items_per_row) * a.fpi;
+    const int f1 = min(f0 + a.fpi, a.frames);
+    const float* xr = a.x + (size_t)row * a.T;
+    const float* yr = a.y + (size_t)row * a.T;
+    for (int f = f0; f < f1; ++f) {
+      float ar[G::R1], ai[G::R1], br[G::R2], bi[G::R2], pr[G::R2], pi[G::R2];
+      if (t < G::R2) {
+        const long long base = (long long)f * G::HOP + t;
+#pragma unroll
+        for (int n1 = 0; n1 < G::R1; ++n1) {
+          const long long p = base + (long long)G::R2 * n1;
+          const float w = sm.win[G::R2 * n1 + t];
+          float xv = 0.f, yv = 0.f;
+          if (p < a.T) {
+            xv = __ldg(xr + p);
+            yv = __ldg(yr + p);
+            if (a.mode == 1) {
+              const int blk = f + (n1 >= G::R1 / 2 ? 1 : 0);
+              const int r = (n1 % (G::R1 / 2)) * G::R2 + t;
+              const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+              yv = __fdiv_rn(yv, ola_env(blk, a.frames, wl * wl, wh * wh));
+            }
+          }
+          ar[n1] = xv * w; ai[n1] = yv * w;
+        }
+      }
+      fwd_pair<G>(ar, ai, br, bi, ex, sm.tw, t, bar);
+      group_sync<G::TPF>(bar);
+      mirror_exchange<G>(br, bi, pr, pi, ex, t, bar);
+      if (t < G::R1) {
+#pragma unroll
+        for (int k2 = 0; k2 <= G::R2 / 2; ++k2) {
+          if (k2 == G::R2 / 2 && t != 0) continue;
+          const int k = t + G::R1 * k2;
+          const float xre = 0.5f * (br[k2] + pr[k2]), xim = 0.5f * (bi[k2] - pi[k2]);
+          const float yre = 0.5f * (bi[k2] + pi[k2]), yim = -0.5f * (br[k2] - pr[k2]);
+          if (a.mode == 0) {
+            const float sx = xre * xre + xim * xim, sy = yre * yre + yim * yim;
+            acc[k] += sx;
+            acc[G::F + k] += sqrtf(sx) * sqrtf(sy);
+            acc[2 * G::F + k] += sy;
+          } else {
+            acc[k] += xre * yre + xim * yim;
+          }
+        }
+      }
+      group_sync<G::TPF>(bar);
+    }
+  }
+  __syncthreads();
+  float* out = a.partial + ((size_t)blockIdx.x * GROUPS + grp) * 3 * G::F;
+  for (int i = t; i < 3 * G::F; i += G::TPF) out[i] = acc[i];
+}
+
+__global__ void k_reduce_stats(const float* partial, int n_partials, int n, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int p = 0; p < n_partials; ++p) s += (double)partial[(size_t)p * n + i];
+  out[i] = s;
+}
+
+// ---------------------------------------------------------------------------
+// K3: standalone STFT   x[B,T] -> X[B,F,frames,2]   (two frames per transform)
+// ---------------------------------------------------------------------------
+struct StftArgs {
+  const float* x; float* X; int B, T;
+  const float* window; const float2* twiddle;
+  int in_env_div; const float* bin_scale;
+  int frames; int ppi; int items_per_row;   // frame pairs per item
+};
+
+template <class G, int GROUPS>
+__global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft(const StftArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<G> sm(smem_raw, GROUPS);
+  load_tables(sm, a.window, a.twiddle);
+  for (int k = threadIdx.x; k < G::F; k += blockDim.x) sm.hs[k] = a.bin_scale ? a.bin_scale[k] : 1.0f;
+  __syncthreads();
+  const int grp = threadIdx.x / G::TPF;
+  const int t = threadIdx.x % G::TPF;
+  const int bar = 1 + grp;
+  float2* ex = sm.ex + grp * G::EX_ELEMS;
+  const long long n_items = (long long)a.B * a.items_per_row;
+  for (long long item = (long long)blockIdx.x * GROUPS + grp; item < n_items;
+       item += (long long)gridDim.x * GROUPS) {
+    const int row = (int)(item / a.items_per_row);
+    const int p0 = (int)(item % a.items_per_row) * a.ppi;
+    const float* xr = a.x + (size_t)row * a.T;
+    float2* Xr = reinterpret_cast<float2*>(a.X) + (size_t)row * G::F * a.frames;
+    for (int pp = p0; pp < p0 + a.ppi && 2 * pp < a.frames; ++pp) {
+      const int fA = 2 * pp;
+      const bool hasB = fA + 1 < a.frames;
+      float ar[G::R1], ai[G::R1], br[G::R2], bi[G::R2], pr[G::R2], pi[G::R2];
+      if (t < G::R2) {
+        float xs[G::R1 + G::R1 / 2];
+        const long long base = (long long)fA * G::HOP + t;
+#pragma unroll
+        for (int j = 0; j < G::R1 + G::R1 / 2; ++j) {
+          const long long p = base + (long long)G::R2 * j;
+          float v = (p < a.T) ? __ldg(xr + p) : 0.f;
+          if (a.in_env_div && p < a.T) {
+            const int blk = fA + j / (G::R1 / 2);
+            const int r = (j % (G::R1 / 2)) * G::R2 + t;
+            const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+            v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
+          }
+          xs[j] = v;
+        }
+#pragma unroll
+        for (int n1 = 0; n1 < G::R1; ++n1) {
+          const float w = sm.win[G::R2 * n1 + t];
+          ar[n1] = xs[n1] * w;
+          ai[n1] = hasB ? xs[n1 + G::R1 / 2] * w : 0.f;
+        }
+      }
+      fwd_pair<G>(ar, ai, br, bi, ex, sm.tw, t, bar);
+      group_sync<G::TPF>(bar);
+      mirror_exchange<G>(br, bi, pr, pi, ex, t, bar);
+      if (t < G::R1) {
+#pragma unroll
+        for (int k2 = 0; k2 <= G::R2 / 2; ++k2) {
+          if (k2 == G::R2 / 2 && t != 0) continue;
+          const int k = t + G::R1 * k2;
+          const float s = sm.hs[k];
+          // frame A = (Z + conj(Zp))/2, frame B = (Z - conj(Zp))/(2i)
+          float2 XA, XB;
+          XA.x = 0.5f * (br[k2] + pr[k2]) * s; XA.y = 0.5f * (bi[k2] - pi[k2]) * s;
+          XB.x = 0.5f * (bi[k2] + pi[k2]) * s; XB.y = -0.5f * (br[k2] - pr[k2]) * s;
+          float2* dst = Xr + (size_t)k * a.frames + fA;
+          dst[0] = XA;
+          if (hasB) dst[1] = XB;
+        }
+      }
+      group_sync<G::TPF>(bar);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4: standalone (filter +) iSTFT   X[B,F,frames,2] -> y[B,out_len]
+// ---------------------------------------------------------------------------
+struct IstftArgs {
+  const float* X; float* y; int B; int frames; int out_len;
+  const float* window; const float2* twiddle;
+  const float* bin_scale; int out_env_div;
+  int bpi; int items_per_row; int nblk;
+};
+
+template <class G, int GROUPS>
+__global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_istft(const IstftArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<G> sm(smem_raw, GROUPS);
+  load_tables(sm, a.window, a.twiddle);
+  constexpr float inv_n = 1.0f / G::N;
+  for (int k = threadIdx.x; k < G::F; k += blockDim.x)
+    sm.hs[k] = (a.bin_scale ? a.bin_scale[k] : 1.0f) * inv_n;
+  __syncthreads();
+  const int grp = threadIdx.x / G::TPF;
+  const int t = threadIdx.x % G::TPF;
+  const int bar = 1 + grp;
+  float2* ex = sm.ex + grp * G::EX_ELEMS;
+  const long long n_items = (long long)a.B * a.items_per_row;
+  for (long long item = (long long)blockIdx.x * GROUPS + grp; item < n_items;
+       item += (long long)gridDim.x * GROUPS) {
+    const int row = (int)(item / a.items_per_row);
+    const int j0 = (int)(item % a.items_per_row) * a.bpi;
+    const int j1 = min(j0 + a.bpi, a.nblk);
+    const int fs = max(j0 - 1, 0);
+    const int fe = min(j1 - 1, a.frames - 1);
+    const float2* Xr = reinterpret_cast<const float2*>(a.X) + (size_t)row * G::F * a.frames;
+    float* yr = a.y + (size_t)row * a.out_len;
+    float carry[G::R1 / 2];
+#pragma unroll
+    for (int i = 0; i < G::R1 / 2; ++i) carry[i] = 0.f;
+    for (int fA = fs; fA <= fe; fA += 2) {
+      float ar[G::R1], ai[G::R1], br[G::R2], bi[G::R2];
+      const bool hasB = fA + 1 < a.frames;
+      if (t < G::R1) {
+#pragma unroll
+        for (int k2 = 0; k2 < G::R2; ++k2) {
+          const int k = t + G::R1 * k2;
+          const bool mir = k > G::N / 2;
+          const int kk = mir ? G::N - k : k;
+          const float2* src = Xr + (size_t)kk * a.frames + fA;
+          float2 XA = src[0];
+          float2 XB = hasB ? src[1] : make_float2(0.f, 0.f);
+          if (kk == 0 || kk == G::N / 2) { XA.y = 0.f; XB.y = 0.f; }   // c2r ignores these
+          if (mir) { XA.y = -XA.y; XB.y = -XB.y; }
+          const float h = sm.hs[kk];
+          br[k2] = (XA.x - XB.y) * h;
+          bi[k2] = (XA.y + XB.x) * h;
+        }
+      }
+      inv_pair<G>(br, bi, ar, ai, ex, sm.tw, t, bar);
+      if (t < G::R2) {
+#pragma unroll
+        for (int n1 = 0; n1 < G::R1; ++n1) {
+          const float w = sm.win[G::R2 * n1 + t];
+          ar[n1] *= w; ai[n1] *= w;
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int blk = fA + half;
+          const bool mine = (blk >= j0) && (blk < j1);
+#pragma unroll
+          for (int n1 = 0; n1 < G::R1 / 2; ++n1) {
+            float v = half == 0 ? __fadd_rn(ar[n1], carry[n1])
+                                : __fadd_rn(ar[n1 + G::R1 / 2], ai[n1]);
+            const int r = G::R2 * n1 + t;
+            const long long p = (long long)blk * G::HOP + r;
+            if (mine && p < a.out_len) {
+              if (a.out_env_div) {
+                const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+                v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
+              }
+              yr[p] = v;
+            }
+          }
+        }
+#pragma unroll
+        for (int n1 = 0; n1 < G::R1 / 2; ++n1) carry[n1] = ai[n1 + G::R1 / 2];
+      }
+      group_sync<G::TPF>(bar);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int pick_chunk(long long rows, int units_per_row, long long capacity, int max_chunk,
+                      bool odd_only) {
+  // chunk size (units per work item) minimising (rounds * cost per item)
+  int best = 1;
+  double best_cost = 1e300;
+  for (int c = 1; c <= max_chunk; ++c) {
+    if (odd_only && (c % 2 == 0)) continue;
+    const long long items = rows * ((units_per_row + c - 1) / c);
+    const long long rounds = (items + capacity - 1) / capacity;
+    const double per_item = odd_only ? (c + 1) * 0.5 : (double)c;  // frame pairs per item
+    const double cost = rounds * per_item * (1.0 + 1e-3 / c);
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+template <class G, int GROUPS>
+static int launch_apply_filter(FilterArgs a, cudaStream_t st) {
+  const int hop = G::HOP;
+  a.frames = 1 + a.T / hop;
+  a.nblk = (a.T - 1) / hop + 1;
+  const int sms = sm_count();
+  a.bpi = pick_chunk(a.B, a.nblk, (long long)sms * GROUPS, 31, true);
+  a.items_per_row = (a.nblk + a.bpi - 1) / a.bpi;
+  const long long items = (long long)a.B * a.items_per_row;
+  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
+  const size_t smem = Smem<G>::bytes(GROUPS);
+  auto kern = k_apply_filter<G, GROUPS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, G::TPF * GROUPS, smem, st>>>(a);
+  return check_launch("k_apply_filter");
+}
+
+template <class G, int GROUPS>
+static int launch_stats(StatsArgs a, double* abc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  a.frames = 1 + a.T / G::HOP;
+  const int sms = sm_count();
+  a.fpi = pick_chunk(a.B, a.frames, (long long)sms * GROUPS, 32, false);
+  a.items_per_row = (a.frames + a.fpi - 1) / a.fpi;
+  const long long items = (long long)a.B * a.items_per_row;
+  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
+  const size_t need = (size_t)grid * GROUPS * 3 * G::F * sizeof(float);
+  BABE_REQUIRE(ws != nullptr && ws_bytes >= need, BABE_EBADARG,
+               "stft_stats: workspace too small (%zu < %zu)", ws_bytes, need);
+  a.partial = static_cast<float*>(ws);
+  const size_t smem = Smem<G>::bytes(GROUPS, 3 * G::F);
+  auto kern = k_stft_stats<G, GROUPS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, G::TPF * GROUPS, smem, st>>>(a);
+  int rc = check_launch("k_stft_stats");
+  if (rc) return rc;
+  const int n = 3 * G::F;
+  k_reduce_stats<<<(n + 255) / 256, 256, 0, st>>>(a.partial, grid * GROUPS, n, abc);
+  return check_launch("k_reduce_stats");
+}
+
+template <class G, int GROUPS>
+static int launch_stft(StftArgs a, cudaStream_t st) {
+  if (a.frames <= 0) a.frames = 1 + a.T / G::HOP;
+  const int pairs = (a.frames + 1) / 2;
+  const int sms = sm_count();
+  a.ppi = pick_chunk(a.B, pairs, (long long)sms * GROUPS, 16, false);
+  a.items_per_row = (pairs + a.ppi - 1) / a.ppi;
+  const long long items = (long long)a.B * a.items_per_row;
+  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
+  const size_t smem = Smem<G>::bytes(GROUPS);
+  auto kern = k_stft<G, GROUPS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, G::TPF * GROUPS, smem, st>>>(a);
+  return check_launch("k_stft");
+}
+
+template <class G, int GROUPS>
+static int launch_istft(IstftArgs a, cudaStream_t st) {
+  a.nblk = (a.out_len - 1) / G::HOP + 1;
+  const int sms = sm_count();
+  a.bpi = pick_chunk(a.B, a.nblk, (long long)sms * GROUPS, 31, true);
+  a.items_per_row = (a.nblk + a.bpi - 1) / a.bpi;
+  const long long items = (long long)a.B * a.items_per_row;
+  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
+  const size_t smem = Smem<G>::bytes(GROUPS);
+  auto kern = k_istft<G, GROUPS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<grid, G::TPF * GROUPS, smem, st>>>(a);
+  return check_launch("k_istft");
+}
+
+// groups per CTA chosen so that one CTA fills an SM's register file / smem
+#define BABE_DISPATCH_NFFT(nfft, CALL)                                   \
+  switch (nfft) {                                                        \
+    case 4096: { using G = Geo<64, 64>; constexpr int GR = 4; CALL; }    \
+    case 2048: { using G = Geo<32, 64>; constexpr int GR = 4; CALL; }    \
+    case 1024: { using G = Geo<32, 32>; constexpr int GR = 8; CALL; }    \
+    case 512:  { using G = Geo<16, 32>; constexpr int GR = 8; CALL; }    \
+    default: break;                                                      \
+  }
+
+}  // namespace babe
+
+using namespace babe;
+
+extern "C" int babe_stft_supported(int nfft) {
+  return nfft == 512 || nfft == 1024 || nfft == 2048 || nfft == 4096;
+}
+
+extern "C" int babe_stft_tables_host(int nfft, float* window_host, float* twiddle_host) {
+  BABE_REQUIRE(babe_stft_supported(nfft), BABE_EUNSUPPORTED, "unsupported NFFT %d", nfft);
+  BABE_REQUIRE(window_host && twiddle_host, BABE_EBADARG, "null table pointer");
+  int r1 = 0, r2 = 0;
+  switch (nfft) {
+    case 4096: r1 = 64; r2 = 64; break;
+    case 2048: r1 = 32; r2 = 64; break;
+    case 1024: r1 = 32; r2 = 32; break;
+    default: r1 = 16; r2 = 32; break;
+  }
+  for (int n = 0; n < nfft; ++n)
+    window_host[n] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * (double)n / (double)nfft));
+  for (int k1 = 0; k1 < r1; ++k1)
+    for (int n2 = 0; n2 < r2; ++n2) {
+      const double ang = -2.0 * M_PI * (double)((long long)k1 * n2 % nfft) / (double)nfft;
+      twiddle_host[2 * (k1 * r2 + n2)] = (float)cos(ang);
+      twiddle_host[2 * (k1 * r2 + n2) + 1] = (float)sin(ang);
+    }
+  return BABE_OK;
+}
+
+extern "C" int babe_apply_filter(const float* x, float* y, int B, int T, int nfft,
+                                 const float* window, const float* twiddle,
+                                 const float* H, const float* freqs, const float* fc,
+                                 const float* A, int K, int adjoint, const float* sub,
+                                 const float* row_scale, double* row_sumsq, int* status,
+                                 void* stream) {
+  BABE_REQUIRE(x && y && window && twiddle, BABE_EBADARG, "apply_filter: null pointer");
+  BABE_REQUIRE(B >= 0 && T >= 0, BABE_EBADARG, "apply_filter: bad shape B=%d T=%d", B, T);
+  BABE_REQUIRE(H != nullptr || (freqs && fc && A && K >= 1 && K <= BABE_MAX_BREAKPOINTS),
+               BABE_EBADARG, "apply_filter: need H or (freqs, fc, A, 1<=K<=%d)", BABE_MAX_BREAKPOINTS);
+  BABE_REQUIRE(babe_stft_supported(nfft), BABE_EUNSUPPORTED, "unsupported NFFT %d", nfft);
+  if (B == 0 || T == 0) return BABE_OK;
+  FilterArgs a{};
+  a.x = x; a.y = y; a.B = B; a.T = T; a.window = window;
+  a.twiddle = reinterpret_cast<const float2*>(twiddle);
+  a.H = H; a.freqs = freqs; a.fc = fc; a.A = A; a.K = K; a.adjoint = adjoint;
+  a.sub = adjoint ? nullptr : sub; a.row_scale = row_scale; a.row_sumsq = row_sumsq;
+  a.status = status;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BABE_DISPATCH_NFFT(nfft, return (launch_apply_filter<G, GR>(a, st)));
+  return BABE_EUNSUPPORTED;
+}
+
+extern "C" size_t babe_stft_stats_workspace(int B, int T, int nfft) {
+  (void)B; (void)T;
+  if (!babe_stft_supported(nfft)) return 0;
+  const int sms = sm_count();
+  return (size_t)sms * 8 * 3 * (nfft / 2 + 1) * sizeof(float);
+}
+
+extern "C" int babe_stft_stats(const float* x, const float* y, int B, int T, int nfft,
+                               const float* window, const float* twiddle, int mode,
+                               double* abc, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  BABE_REQUIRE(x && y && window && twiddle && abc, BABE_EBADARG, "stft_stats: null pointer");
+  BABE_REQUIRE(B >= 1 && T >= 1, BABE_EBADARG, "stft_stats: bad shape B=%d T=%d", B, T);
+  BABE_REQUIRE(mode == 0 || mode == 1, BABE_EBADARG, "stft_stats: bad mode %d", mode);
+  BABE_REQUIRE(babe_stft_supported(nfft), BABE_EUNSUPPORTED, "unsupported NFFT %d", nfft);
+  StatsArgs a{};
+  a.x = x; a.y = y; a.B = B; a.T = T; a.window = window;
+  a.twiddle = reinterpret_cast<const float2*>(twiddle); a.mode = mode;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (nfft) {
+    case 4096: return launch_stats<Geo<64, 64>, 3>(a, abc, workspace, workspace_bytes, st);
+    case 2048: return launch_stats<Geo<32, 64>, 4>(a, abc, workspace, workspace_bytes, st);
+    case 1024: return launch_stats<Geo<32, 32>, 8>(a, abc, workspace, workspace_bytes, st);
+    case 512: return launch_stats<Geo<16, 32>, 8>(a, abc, workspace, workspace_bytes, st);
+  }
+  return BABE_EUNSUPPORTED;
+}
+
+extern "C" int babe_stft(const float* x, float* X, int B, int T, int nfft, int frames,
+                         const float* window, const float* twiddle, int in_env_div,
+                         const float* bin_scale, void* stream) {
+  BABE_REQUIRE(x && X && window && twiddle, BABE_EBADARG, "stft: null pointer");
+  BABE_REQUIRE(B >= 0 && T >= 0, BABE_EBADARG, "stft: bad shape B=%d T=%d", B, T);
+  BABE_REQUIRE(babe_stft_supported(nfft), BABE_EUNSUPPORTED, "unsupported NFFT %d", nfft);
+  if (B == 0) return BABE_OK;
+  StftArgs a{};
+  a.x = x; a.X = X; a.B = B; a.T = T; a.window = window;
+  a.twiddle = reinterpret_cast<const float2*>(twiddle);
+  a.in_env_div = in_env_div; a.bin_scale = bin_scale; a.frames = frames;
+  BABE_REQUIRE(frames >= 0 && frames <= 1 + T / (nfft / 2), BABE_EBADARG,
+               "stft: frames=%d out of range", frames);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BABE_DISPATCH_NFFT(nfft, return (launch_stft<G, GR>(a, st)));
+  return BABE_EUNSUPPORTED;
+}
+
+extern "C" int babe_istft(const float* X, float* y, int B, int frames, int nfft, int out_len,
+                          const float* window, const float* twiddle, const float* bin_scale,
+                          int out_env_div, void* stream) {
+  BABE_REQUIRE(X && y && window && twiddle, BABE_EBADARG, "istft: null pointer");
+  BABE_REQUIRE(babe_stft_supported(nfft), BABE_EUNSUPPORTED, "unsupported NFFT %d", nfft);
+  BABE_REQUIRE(B >= 0 && frames >= 1, BABE_EBADARG, "istft: bad shape B=%d frames=%d", B, frames);
+  BABE_REQUIRE(out_len >= 1 && out_len <= nfft + (nfft / 2) * (frames - 1), BABE_EBADARG,
+               "istft: out_len %d out of range", out_len);
+  if (B == 0) return BABE_OK;
+  IstftArgs a{};
+  a.X = X; a.y = y; a.B = B; a.frames = frames; a.out_len = out_len; a.window = window;
+  a.twiddle = reinterpret_cast<const float2*>(twiddle);
+  a.bin_scale = bin_scale; a.out_env_div = out_env_div;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BABE_DISPATCH_NFFT(nfft, return (launch_istft<G, GR>(a, st)));
+  return BABE_EUNSUPPORTED;
+}

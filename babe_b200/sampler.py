@@ -1,0 +1,419 @@
+"""Blind bandwidth-extension posterior sampler on the CUDA operator.
+
+``BlindSamplerFused`` is a drop-in for ``tester.sampler_callable``
+('testing.blind_bwe_sampler.BlindSampler' in conf/tester/blind_bwe.yaml:9): same
+constructor ``(model, diff_params, args, rid)`` and the same
+``predict_blind_bwe`` / ``predict_bwe`` / ``predict_unconditional`` methods and
+return tuples (testing/blind_bwe_sampler.py:14,306,366,619).  Differences are
+purely in execution:
+
+* the per-step filter re-estimation runs as ONE statistics pass over
+  (x_den, y) plus ONE device-resident kernel doing all <=100 projected
+  gradient iterations (reference: a Python loop of ~25 launches and >=K+2 host
+  syncs per iteration, testing/blind_bwe_sampler.py:562-590);
+* the reconstruction-guidance loss and its cotangent are two fused launches
+  (filter-design + STFT + multiply + iSTFT + residual + row norms; adjoint)
+  and H(fc, A) is never written to HBM;
+* noise may be drawn on the device (``device_noise=True``); the default keeps
+  the reference's host generator stream so that outputs are comparable for a
+  fixed ``torch.manual_seed``.
+"""
+import types
+
+import torch
+
+from . import blind_bwe_utils as bu
+from . import ops
+from ._lib import FitConfig
+
+
+# ---------------------------------------------------------------------------
+# args shim (Hydra/OmegaConf are not installed)
+# ---------------------------------------------------------------------------
+def _ns(**kw):
+    return types.SimpleNamespace(**kw)
+
+
+def make_args(sample_rate=22050, audio_len=184184, T=35, xi=0.2, start_sigma=0.2,
+              NFFT=4096, fc_init=(280, 285, 290, 295, 300), A_init=(-15, -17, -20, -25, -30),
+              max_iter=100, Schurn=20, num_octs=7, bins_per_oct=64, **extra):
+    """Nested attribute namespace carrying exactly the fields the sampler, EDM
+    and the CQTDiff+ constructor read, with the values of
+    conf/tester/blind_bwe.yaml, conf/exp/maestro22k_8s.yaml,
+    conf/diff_params/edm.yaml and conf/network/cqtdiff+.yaml."""
+    args = _ns(
+        exp=_ns(sample_rate=sample_rate, audio_len=audio_len, seed=42),
+        diff_params=_ns(callable="babe_b200.edm.EDM", sigma_data=0.063, sigma_min=1e-5,
+                        sigma_max=10, P_mean=-1.2, P_std=1.2, ro=13, ro_train=13, Schurn=5,
+                        Snoise=1, Stmin=0, Stmax=50,
+                        aweighting=_ns(use_aweighting=False, ntaps=101)),
+        network=_ns(callable="babe_b200.denoiser.CQTDiffPlus", use_fencoding=False, use_norm=True,
+                    emb_dim=256, Ns=[64, 96, 96, 128, 128, 256, 256], Ss=[2] * 7,
+                    num_dils=[2, 3, 4, 5, 6, 7, 7], attention_layers=[0] * 8,
+                    bottleneck_type="res_dil_convs", num_bottleneck_layers=1,
+                    cqt=_ns(window="kaiser", beta=1, num_octs=num_octs, bins_per_oct=bins_per_oct),
+                    attention_dict=_ns(num_heads=8, attn_dropout=0.0, bias_qkv=False, N=0,
+                                       rel_pos_num_buckets=32, rel_pos_max_distance=64,
+                                       use_rel_pos=True, Nproj=8)),
+        tester=_ns(
+            sampler_callable="babe_b200.sampler.BlindSamplerFused",
+            T=T, order=2, filter_out_cqt_DC_Nyq=True,
+            diff_params=_ns(same_as_training=False, sigma_data=0.063, sigma_min=1e-4, sigma_max=1,
+                            ro=8, Schurn=Schurn, Snoise=1.0, Stmin=0, Stmax=50),
+            posterior_sampling=_ns(xi=xi, data_consistency=False, norm=2, smoothl1_beta=1,
+                                   SNR_observations="None", start_sigma=start_sigma,
+                                   freq_weighting="None", freq_weighting_filter="sqrt",
+                                   stft_distance=_ns(use=False, mag=False, use_multires=False,
+                                                     nfft=2048, logmag=False)),
+            blind_bwe=_ns(fcmin=20, fcmax="nyquist", Amin=-50, Amax=30, NFFT=NFFT,
+                          sigma_den_estimate=0.0,
+                          test_filter=_ns(fc=[1000], A=[-20]),
+                          initial_conditions=_ns(fc=list(fc_init), A=list(A_init)),
+                          optimization=_ns(max_iter=max_iter, tol=[5e-3, 5e-3], mu=[1000, 10],
+                                           clamp_fc=True, clamp_A=True, only_negative_A=True)),
+            complete_recording=_ns(n_segments_blindstep=2, std=0.1, overlap=0.25, inpaint_DC=True),
+        ),
+    )
+    for k, v in extra.items():
+        setattr(args, k, v)
+    return args
+
+
+# ---------------------------------------------------------------------------
+# a7: filter fit = one statistics pass + one device-resident loop
+# ---------------------------------------------------------------------------
+class FilterFit:
+    """BlindSampler.fit_params (testing/blind_bwe_sampler.py:533-595)."""
+
+    def __init__(self, nfft=4096, sample_rate=22050, fcmin=20, fcmax="nyquist", Amin=-50, Amax=30,
+                 max_iter=100, tol=(5e-3, 5e-3), mu=(1000, 10), clamp_fc=True, clamp_A=True,
+                 only_negative_A=True, freq_weighting="sqrt", device="cuda"):
+        self.nfft = int(nfft)
+        fcmax_v = sample_rate // 2 if fcmax == "nyquist" else fcmax   # :35-38 (integer division)
+        self.cfg = FitConfig(mu_fc=mu[0], mu_A=mu[1], fcmin=fcmin, fcmax=fcmax_v, Amin=Amin, Amax=Amax,
+                             tol_fc=tol[0], tol_A=tol[1], max_iter=int(max_iter),
+                             clamp_fc=int(bool(clamp_fc)), clamp_A=int(bool(clamp_A)),
+                             only_negative_A=int(bool(only_negative_A)))
+        self.freqs = torch.fft.rfftfreq(self.nfft, d=1 / sample_rate).to(device)   # :629
+        w = bu.freq_weight_vector(freq_weighting, self.nfft // 2 + 1, device)
+        self.w = w if w is not None else torch.ones(self.nfft // 2 + 1, device=device)
+
+    @classmethod
+    def from_args(cls, args, device):
+        b, o = args.tester.blind_bwe, args.tester.blind_bwe.optimization
+        return cls(nfft=b.NFFT, sample_rate=args.exp.sample_rate, fcmin=b.fcmin, fcmax=b.fcmax,
+                   Amin=b.Amin, Amax=b.Amax, max_iter=o.max_iter, tol=o.tol, mu=o.mu,
+                   clamp_fc=o.clamp_fc, clamp_A=o.clamp_A, only_negative_A=o.only_negative_A,
+                   freq_weighting=args.tester.posterior_sampling.freq_weighting_filter, device=device)
+
+    def stats(self, x_den, y):
+        return ops.stft_stats(x_den, y, self.nfft, mode=0)
+
+    def __call__(self, x_den, y, params, return_iters=False, abc=None):
+        """params (2,K) is updated in place (the reference also mutates it,
+        testing/blind_bwe_sampler.py:577-583) and returned."""
+        if abc is None:
+            abc = self.stats(x_den, y)
+        return ops.fit_params(abc, self.w, self.freqs, params, self.cfg, return_iters=return_iters)
+
+
+# ---------------------------------------------------------------------------
+# a8: fused reconstruction-guidance loss
+# ---------------------------------------------------------------------------
+class _RecGuidanceNorm(torch.autograd.Function):
+    """norm_b = || y_b - A_{fc,A}(x_b) ||_2  (testing/blind_bwe_sampler.py:89,117)
+    with backward  g_b * A^T((A x_b - y_b) / norm_b)  (what :120 back-propagates
+    into the denoiser).  H is designed inside both kernels."""
+
+    @staticmethod
+    def forward(ctx, x, y, freqs, fc, A, nfft):
+        ss = torch.zeros(x.shape[0], dtype=torch.float64, device=x.device)
+        r = ops.apply_filter(x, nfft, freqs=freqs, fc=fc, A=A, sub=y, row_sumsq=ss)
+        norms = torch.sqrt(ss).to(torch.float32)
+        ctx.save_for_backward(r, norms, freqs, fc, A)
+        ctx.nfft = nfft
+        return norms
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        r, norms, freqs, fc, A = ctx.saved_tensors
+        scale = (g / norms).contiguous()
+        gx = ops.apply_filter(r, ctx.nfft, freqs=freqs, fc=fc, A=A, adjoint=True, row_scale=scale)
+        return gx, None, None, None, None, None
+
+
+def rec_guidance_norms(x, y, freqs, filter_params, nfft):
+    return _RecGuidanceNorm.apply(x, y, freqs, filter_params[0].contiguous(),
+                                  filter_params[1].contiguous(), int(nfft))
+
+
+# ---------------------------------------------------------------------------
+class BlindSamplerFused:
+    def __init__(self, model, diff_params, args, rid=False, device_noise=False):
+        """testing/blind_bwe_sampler.py:14-47."""
+        self.model = model
+        self.diff_params = diff_params
+        self.args = args
+        if not args.tester.diff_params.same_as_training:
+            self.update_diff_params()
+        self.order = args.tester.order
+        self.xi = args.tester.posterior_sampling.xi
+        self.data_consistency = args.tester.posterior_sampling.data_consistency
+        self.nb_steps = args.tester.T
+        self.start_sigma = args.tester.posterior_sampling.start_sigma
+        if self.start_sigma == "None":
+            self.start_sigma = None
+        self.device_noise = device_noise
+        self.generator = None          # optional torch.Generator for device noise
+        self._fit = None
+
+    def update_diff_params(self):
+        """testing/blind_bwe_sampler.py:50-60."""
+        d, s = self.diff_params, self.args.tester.diff_params
+        d.sigma_min, d.sigma_max, d.ro, d.sigma_data = s.sigma_min, s.sigma_max, s.ro, s.sigma_data
+        d.Schurn, d.Stmin, d.Stmax, d.Snoise = s.Schurn, s.Stmin, s.Stmax, s.Snoise
+
+    # -- noise ---------------------------------------------------------------
+    def _randn(self, shape, device):
+        if self.device_noise:
+            return torch.randn(shape, device=device, generator=self.generator)
+        return torch.randn(shape).to(device)       # reference: host generator (:513, edm.py:105)
+
+    def move_timestep(self, x, t, gamma, Snoise=1):
+        """testing/blind_bwe_sampler.py:509-516 (always draws)."""
+        t_hat = t + gamma * t
+        eps = self._randn(x.shape, x.device) * Snoise
+        return x + ((t_hat ** 2 - t ** 2) ** (1 / 2)) * eps, t_hat
+
+    # -- pieces of one evaluation -------------------------------------------------
+    def get_denoised_estimate(self, x, t_i):
+        """testing/blind_bwe_sampler.py:152-157."""
+        x_hat = self.diff_params.denoiser(x, self.model, t_i.unsqueeze(-1))
+        if self.args.tester.filter_out_cqt_DC_Nyq:
+            x_hat = self.model.CQTransform.apply_hpf_DC(x_hat)
+        return x_hat
+
+    def apply_filter_fcA(self, x, filter_params):
+        """testing/blind_bwe_sampler.py:518-520, H designed inside the kernel."""
+        H = bu.design_filter(filter_params[0], filter_params[1], self.freqs)
+        return bu.apply_filter(x, H, self.args.tester.blind_bwe.NFFT)
+
+    def _maybe_noise_observations(self, y):
+        ps = self.args.tester.posterior_sampling
+        if ps.SNR_observations != "None":           # :80-86, :542-548 (in place on y)
+            snr = 10 ** (ps.SNR_observations / 10)
+            sigma = torch.sqrt(torch.var(y, -1) / snr).unsqueeze(-1)
+            y += sigma * self._randn(y.shape, y.device)
+
+    def fit_params(self, denoised_estimate, y, filter_params):
+        """testing/blind_bwe_sampler.py:533-595."""
+        self._maybe_noise_observations(y)
+        sde = self.args.tester.blind_bwe.sigma_den_estimate
+        if sde:
+            denoised_estimate = denoised_estimate + self._randn(denoised_estimate.shape,
+                                                                 denoised_estimate.device) * sde
+        return self._fit(denoised_estimate, y, filter_params)
+
+    def get_rec_grads(self, x_den, y, x, t_i, filter_params):
+        """testing/blind_bwe_sampler.py:75-135."""
+        ps = self.args.tester.posterior_sampling
+        self._maybe_noise_observations(y)
+        nfft = self.args.tester.blind_bwe.NFFT
+        if ps.norm == 2 and not ps.stft_distance.use:
+            norm = rec_guidance_norms(x_den, y, self.freqs, filter_params, nfft)
+        else:
+            den_rec = self.apply_filter_fcA(x_den, filter_params)
+            if ps.norm == "smoothl1":
+                norm = torch.nn.functional.smooth_l1_loss(y, den_rec, reduction='sum', beta=ps.smoothl1_beta)
+            elif ps.norm == "cosine":
+                cos = torch.nn.CosineSimilarity(dim=1, eps=1e-6)
+                norm = (1 - cos(den_rec, y)).clamp(min=0)
+            elif ps.stft_distance.use:
+                if ps.stft_distance.use_multires:
+                    raise NotImplementedError("multires STFT distance is dead code in the reference "
+                                              "(testing/blind_bwe_sampler.py:108 calls a missing self.norm)")
+                if ps.stft_distance.mag:
+                    norm = bu.apply_norm_STFTmag_fweighted(y, den_rec, ps.freq_weighting,
+                                                           ps.stft_distance.nfft,
+                                                           logmag=ps.stft_distance.logmag)
+                else:
+                    norm = bu.apply_norm_STFT_fweighted(y, den_rec, ps.freq_weighting, ps.stft_distance.nfft)
+            else:
+                norm = torch.linalg.norm(y - den_rec, dim=1, ord=ps.norm)
+        (rec_grads,) = torch.autograd.grad(outputs=norm.sum(), inputs=x)
+        normguide = torch.linalg.norm(rec_grads) / self.args.exp.audio_len ** 0.5
+        s = self.xi / (normguide + 1e-6)
+        return s * rec_grads / t_i
+
+    def data_consistency_step_classic(self, x_hat, y, filter_params):
+        """testing/blind_bwe_sampler.py:63-73."""
+        return y + x_hat - self.apply_filter_fcA(x_hat, filter_params)
+
+    def _evaluate(self, x_in, t_in, y, filter_params):
+        """Lines :689-:709 (and :733-:752 for the Heun correction)."""
+        x_in.requires_grad_(True)
+        x_den = self.get_denoised_estimate(x_in, t_in)
+        x_den_2 = x_den.clone().detach()
+        filter_params = self.fit_params(x_den_2, y, filter_params)
+        rec_grads = self.get_rec_grads(x_den, y, x_in, t_in, filter_params)
+        x_in.detach_()
+        score = (x_den_2 - x_in) / t_in ** 2 - rec_grads
+        if self.args.tester.posterior_sampling.data_consistency:
+            x_den_3 = score * t_in ** 2 + x_in
+            x_den_3 = self.data_consistency_step_classic(x_den_3, y, filter_params)
+            score = (x_den_3 - x_in) / t_in ** 2
+        return score, filter_params, x_den_2
+
+    def compute_sweep(self, denoised_estimate, y):
+        """testing/blind_bwe_sampler.py:598-616 on the collapsed statistics."""
+        abc = self._fit.stats(denoised_estimate, y)
+        w2 = self._fit.w.double() ** 2
+        grads = torch.zeros(self.fc_s.shape[0], self.A_s.shape[0], 2)
+        norms = torch.zeros(self.fc_s.shape[0], self.A_s.shape[0])
+        for i in range(self.fc_s.shape[0]):
+            for j in range(self.A_s.shape[0]):
+                fc, A = self.fc_s[i].reshape(1), self.A_s[j].reshape(1)
+                H = ops.design_filter(fc, A, self.freqs, strict=False).double()
+                nrm = torch.sqrt((w2 * (H * H * abc[0] - 2 * H * abc[1] + abc[2])).sum())
+                gH = (w2 * (H * abc[0] - abc[1]) / nrm).float()
+                gfc, gA, _ = ops.design_filter_vjp(fc, A, self.freqs, gH)
+                grads[i, j, 0], grads[i, j, 1], norms[i, j] = gfc[0], gA[0], nrm
+        return norms, grads
+
+    # -- the sampling loop ---------------------------------------------------
+    def predict_blind_bwe(self, y, rid=False, compute_sweep=False, max_steps=None, step_hook=None):
+        """testing/blind_bwe_sampler.py:619-769.  ``max_steps`` bounds the loop
+        (benchmarks); ``step_hook(i, x, filter_params)`` is called after each
+        step."""
+        args = self.args
+        device = y.device
+        self.freqs = torch.fft.rfftfreq(args.tester.blind_bwe.NFFT, d=1 / args.exp.sample_rate).to(device)
+        self._fit = FilterFit.from_args(args, device)
+        shape = y.shape
+        filter_params = torch.Tensor([args.tester.blind_bwe.initial_conditions.fc,
+                                      args.tester.blind_bwe.initial_conditions.A]).to(device)
+        if len(filter_params.shape) == 1:
+            filter_params.unsqueeze_(1)
+        if compute_sweep:
+            self.fc_s = torch.logspace(2.5, 4, 15).to(device)
+            self.A_s = torch.linspace(-80, -5, 12).to(device)
+            if rid:
+                data_norms = torch.zeros((self.nb_steps, self.fc_s.shape[0], self.A_s.shape[0]))
+                data_grads = torch.zeros((self.nb_steps, self.fc_s.shape[0], self.A_s.shape[0], 2))
+        if rid:
+            data_denoised = torch.zeros((self.nb_steps, shape[0], shape[1]))
+            data_filters = torch.zeros((self.nb_steps, *filter_params.shape))
+
+        if self.start_sigma is None:
+            t = self.diff_params.create_schedule(self.nb_steps).to(device)
+            x = self._randn(shape, device) * t[0]
+        else:
+            t = self.diff_params.create_schedule_from_initial_t(self.start_sigma, self.nb_steps).to(device)
+            x = y + self._randn(shape, device) * t[0]
+        gamma = self.diff_params.get_gamma(t).to(device)
+        t_host = t.cpu()
+        n_steps = self.nb_steps if max_steps is None else min(max_steps, self.nb_steps)
+
+        for i in range(n_steps):
+            x_hat, t_hat = self.move_timestep(x, t[i], gamma[i])
+            score, filter_params, x_den_2 = self._evaluate(x_hat, t_hat, y, filter_params)
+            if compute_sweep:
+                norms, grads = self.compute_sweep(x_den_2, y)
+            d = -t_hat * score
+            if rid:
+                data_denoised[i] = x_den_2
+                data_filters[i] = filter_params
+                if compute_sweep:
+                    data_norms[i] = norms
+                    data_grads[i] = grads
+            h = t[i + 1] - t_hat
+            if float(t_host[i + 1]) != 0 and self.order == 2:
+                t_prime = t[i + 1]
+                x_prime = x_hat + h * d
+                score, filter_params, _ = self._evaluate(x_prime, t_prime, y, filter_params)
+                d_prime = -t_prime * score
+                x = x_hat + h * ((1 / 2) * d + (1 / 2) * d_prime)
+            else:
+                x = x_hat + h * d
+            if step_hook is not None:
+                step_hook(i, x, filter_params)
+
+        if rid:
+            out = (x.detach(), filter_params.detach(), data_denoised.detach(), t.detach(), data_filters.detach())
+            if compute_sweep:
+                out = out + (data_norms.detach(), data_grads.detach())
+            return out
+        return x.detach(), filter_params.detach()
+
+    def predict_unconditional(self, shape, device, rid=False):
+        """testing/blind_bwe_sampler.py:366-374,406-497 with y = None."""
+        t = self.diff_params.create_schedule(self.nb_steps).to(device)
+        x = self._randn(shape, device) * t[0]
+        gamma = self.diff_params.get_gamma(t).to(device)
+        t_host = t.cpu()
+        if rid:
+            data_denoised = torch.zeros((self.nb_steps, shape[0], shape[1]))
+            data_score = torch.zeros((self.nb_steps, shape[0], shape[1]))
+        for i in range(self.nb_steps):
+            x_hat, t_hat = self.move_timestep(x, t[i], gamma[i], self.diff_params.Snoise)
+            with torch.no_grad():
+                score = (self.get_denoised_estimate(x_hat, t_hat) - x_hat) / t_hat ** 2
+            d = -t_hat * score
+            if rid:
+                data_denoised[i] = score * t_hat ** 2 + x_hat
+                data_score[i] = score
+            h = t[i + 1] - t_hat
+            if float(t_host[i + 1]) != 0 and self.order == 2:
+                t_prime = t[i + 1]
+                x_prime = x_hat + h * d
+                with torch.no_grad():
+                    score = (self.get_denoised_estimate(x_prime, t_prime) - x_prime) / t_prime ** 2
+                x = x_hat + h * ((1 / 2) * d + (1 / 2) * (-t_prime * score))
+            else:
+                x = x_hat + h * d
+        if rid:
+            return x.detach(), data_denoised.detach(), data_score.detach(), t.detach()
+        return x.detach()
+
+    def predict_bwe(self, ylpf, filt, filt_type, rid=False, test_filter_fit=False, compute_sweep=False):
+        """testing/blind_bwe_sampler.py:306-364, the ``fc_A`` branch (known
+        parametric filter, no re-estimation).  The classical FIR/IIR observation
+        models (utils/bandwidth_extension.py) are outside this path."""
+        if filt_type != "fc_A":
+            raise NotImplementedError(f"filt_type {filt_type!r}: only 'fc_A' runs on the CUDA operator")
+        args = self.args
+        device = ylpf.device
+        self.freqs = torch.fft.rfftfreq(args.tester.blind_bwe.NFFT, d=1 / args.exp.sample_rate).to(device)
+        params = filt.to(device)
+        y = ylpf
+        shape = y.shape
+        if self.start_sigma is None:
+            t = self.diff_params.create_schedule(self.nb_steps).to(device)
+            x = self._randn(shape, device) * t[0]
+        else:
+            t = self.diff_params.create_schedule_from_initial_t(self.start_sigma, self.nb_steps).to(device)
+            x = y + self._randn(shape, device) * t[0]
+        gamma = self.diff_params.get_gamma(t).to(device)
+        t_host = t.cpu()
+
+        def score_fn(x_in, t_in):
+            x_in = x_in.detach().requires_grad_(True)
+            x_den = self.get_denoised_estimate(x_in, t_in)
+            rec = self.get_rec_grads(x_den, y, x_in, t_in, params)
+            x_in = x_in.detach()
+            return (x_den.detach() - x_in) / t_in ** 2 - rec
+
+        for i in range(self.nb_steps):
+            x_hat, t_hat = self.move_timestep(x, t[i], gamma[i], self.diff_params.Snoise)
+            score = score_fn(x_hat, t_hat)
+            d = -t_hat * score
+            h = t[i + 1] - t_hat
+            if float(t_host[i + 1]) != 0 and self.order == 2:
+                t_prime = t[i + 1]
+                x_prime = x_hat + h * d
+                score = score_fn(x_prime, t_prime)
+                x = x_hat + h * ((1 / 2) * d + (1 / 2) * (-t_prime * score))
+            else:
+                x = x_hat + h * d
+        return x.detach()

@@ -1,0 +1,142 @@
+/* babe_b200 -- C ABI of the B200-native blind-BWE signal-processing hot path.
+ *
+ * The reference (eloimoliner/BABE) is pure Python/PyTorch and has no FFI; its
+ * plug-in points are Python module functions (utils/blind_bwe_utils.py) and
+ * the external class cqt_nsgt_pytorch.CQT_nsgt.  This header is the boundary
+ * *beneath* those seams: the Python drop-ins in babe_b200/ bind exactly these
+ * symbols with ctypes, and any other host (C, C++, cgo, JNI) can do the same
+ * -- see INTEGRATION.md for the reference-side stubs.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *    the library never allocates, frees or retains caller memory;
+ *  - float32 data, row-major, contiguous; `stream` is a cudaStream_t passed as
+ *    void* (NULL = legacy default stream); calls are asynchronous;
+ *  - return 0 on success, BABE_EBADARG (-1) for an invalid shape/argument,
+ *    BABE_EUNSUPPORTED (-2) for an unsupported transform length,
+ *    BABE_ECUDA (-3) for a CUDA error; babe_last_error() gives the message
+ *    (thread-local);
+ *  - thread-safe for distinct streams.
+ */
+#ifndef BABE_B200_H
+#define BABE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BABE_OK 0
+#define BABE_EBADARG (-1)
+#define BABE_EUNSUPPORTED (-2)
+#define BABE_ECUDA (-3)
+
+#define BABE_MAX_BREAKPOINTS 16
+
+const char* babe_last_error(void);
+int babe_version(void);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int babe_sm_count(void);
+
+/* ---- STFT tables ------------------------------------------------------- */
+/* Supported NFFT: 512, 1024, 2048, 4096 (reference configs use 4096,
+ * 1024 and 2048: conf/tester/*.yaml). Returns 1/0. */
+int babe_stft_supported(int nfft);
+/* Fills HOST arrays: window_host[nfft] = periodic Hamming window
+ * (utils/blind_bwe_utils.py:19), twiddle_host[2*nfft] = interleaved (re,im) of
+ * exp(-2*pi*i*n2*k1/nfft) laid out [k1][n2] for the two-pass in-register FFT.
+ * The caller uploads them once per NFFT and passes the device copies below. */
+int babe_stft_tables_host(int nfft, float* window_host, float* twiddle_host);
+
+/* ---- a4/a5: filter design --------------------------------------------- */
+/* Replaces design_filter / design_filter_G (utils/blind_bwe_utils.py:82-119,
+ * :41-80).  fc[K], A[K] breakpoints, freqs[F] bin frequencies, gain_db
+ * optional 1-element device array (NULL = no gain).  status (optional int*)
+ * is set non-zero when some fc_i (i>=1) lies above freqs[F-1], the case in
+ * which the reference raises IndexError. */
+int babe_design_filter(const float* fc, const float* A, int K, const float* gain_db,
+                       const float* freqs, int F, float* H, int* status, void* stream);
+/* Vector-Jacobian product of the above: given gH[F] = dL/dH returns
+ * gfc[K], gA[K] and (optional) ggain[1]. Replaces the autograd backward the
+ * reference runs at testing/blind_bwe_sampler.py:566. */
+int babe_design_filter_vjp(const float* fc, const float* A, int K, const float* gain_db,
+                           const float* freqs, int F, const float* gH,
+                           float* gfc, float* gA, float* ggain, void* stream);
+
+/* ---- a3/a12: fused STFT -> H -> iSTFT ---------------------------------- */
+/* Replaces apply_filter (utils/blind_bwe_utils.py:6-13) and
+ * BlindSampler.apply_filter_fcA (testing/blind_bwe_sampler.py:518-520).
+ *   x[B,T] -> y[B,T].
+ * The filter is either H[F] (H != NULL) or designed on the fly from
+ * (freqs, fc, A, K) so that H never exists in HBM.
+ * adjoint != 0 computes the transpose wrt x (the autograd backward the
+ * reference runs at testing/blind_bwe_sampler.py:120).
+ * Optional epilogues (any may be NULL):
+ *   sub[B,T]       y <- y - sub                       (forward only)
+ *   row_scale[B]   y <- y * row_scale[b]
+ *   row_sumsq[B]   row_sumsq[b] += sum_t y[b,t]^2     (double, caller zeroes)
+ */
+int babe_apply_filter(const float* x, float* y, int B, int T, int nfft,
+                      const float* window, const float* twiddle,
+                      const float* H, const float* freqs, const float* fc, const float* A, int K,
+                      int adjoint, const float* sub, const float* row_scale, double* row_sumsq,
+                      int* status, void* stream);
+
+/* ---- a1: STFT, a2: filter + iSTFT (unfused signatures) ------------------ */
+/* apply_stft (utils/blind_bwe_utils.py:15-26): x[B,T] -> X[B,F,frames,2].
+ * frames = 0 means the reference's 1 + T/(nfft/2) (x is treated as right
+ * padded with nfft zeros); an explicit smaller count frames the first
+ * nfft + (nfft/2)(frames-1) samples only.  in_env_div: divide the input by
+ * the overlap-add envelope of `frames` frames first; bin_scale[F] optional
+ * per-bin real factor (both are used by the backward of babe_istft). */
+int babe_stft(const float* x, float* X, int B, int T, int nfft, int frames,
+              const float* window, const float* twiddle,
+              int in_env_div, const float* bin_scale, void* stream);
+/* apply_filter_istft (utils/blind_bwe_utils.py:28-39): X[B,F,frames,2], H[F]
+ * (NULL = 1) -> y[B,out_len], out_len <= nfft + (nfft/2)(frames-1).
+ * out_env_div=1 reproduces torch.istft; 0 with bin_scale = N*c_k gives the
+ * adjoint of babe_stft. */
+int babe_istft(const float* X, float* y, int B, int frames, int nfft, int out_len,
+               const float* window, const float* twiddle,
+               const float* bin_scale, int out_env_div, void* stream);
+
+/* ---- fit statistics (a6 collapsed) ------------------ */
+/* mode 0: abc[0..F) = sum|X|^2, abc[F..2F) = sum|X||Y|, abc[2F..3F) = sum|Y|^2
+ *         over batch and frames, X = STFT(x), Y = STFT(y);
+ * mode 1: abc[0..F) = sum Re(conj(X) G), G = STFT(y / envelope)  (dL/dH of
+ *         apply_filter up to the rfft weights), the rest is zero.
+ * abc is double[3F].  workspace: babe_stft_stats_workspace() bytes. */
+size_t babe_stft_stats_workspace(int B, int T, int nfft);
+int babe_stft_stats(const float* x, const float* y, int B, int T, int nfft,
+                    const float* window, const float* twiddle, int mode,
+                    double* abc, void* workspace, size_t workspace_bytes, void* stream);
+/* Same statistics from precomputed spectrograms X, Xref [B,F,frames,2] as the
+ * reference signature apply_filter_and_norm_STFTmag_fweighted(X, Xref, H, w)
+ * (utils/blind_bwe_utils.py:250-296) receives them.  out is double[4F]:
+ * a, b, c and s_k = sum_{b,t} (w_k (H_k |X| - |Xref|))^2 (H, w may be NULL = 1). */
+int babe_spec_mag_stats(const float* X, const float* Xref, const float* H, const float* w,
+                        int B, int F, int frames, double* out, void* stream);
+
+/* ---- a7: device-resident filter fit ------------------------------------ */
+/* Replaces the Python loop of BlindSampler.fit_params
+ * (testing/blind_bwe_sampler.py:562-590): projected gradient descent on
+ * params[2,K] (row 0 = fc, row 1 = A; updated IN PLACE like the reference)
+ * with the loss sqrt(sum_k w_k^2 (H_k^2 a_k - 2 H_k b_k + c_k)).
+ * iters_out (optional int*) receives the number of iterations run. */
+typedef struct {
+  float mu_fc, mu_A;       /* step sizes, optimization.mu             */
+  float fcmin, fcmax;      /* blind_bwe.fcmin, sample_rate//2          */
+  float Amin, Amax;        /* blind_bwe.Amin / Amax                    */
+  float tol_fc, tol_A;     /* optimization.tol                         */
+  int max_iter;            /* optimization.max_iter                    */
+  int clamp_fc, clamp_A, only_negative_A;
+} babe_fit_config;
+int babe_fit_params(const double* abc, const float* w, const float* freqs, int F,
+                    float* params, int K, const babe_fit_config* cfg_host,
+                    int* iters_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BABE_B200_H */

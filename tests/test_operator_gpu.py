@@ -1,0 +1,243 @@
+"""GPU parity: the CUDA operator (through the C ABI and the drop-in module)
+against the oracle on identical seeded inputs, against the golden vectors the
+reference produced, and -- at full BASELINE sizes -- through size-independent
+properties.  Tolerance: relative L2 <= 1e-5 in fp32 (BASELINE.json north_star)
+unless a test states otherwise."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def bu():
+    from babe_b200 import build
+    build.build()
+    from babe_b200 import blind_bwe_utils
+    return blind_bwe_utils
+
+
+@pytest.fixture(scope="module")
+def sf():
+    from oracle import stft_filter
+    return stft_filter
+
+
+def cuda(a):
+    return torch.as_tensor(np.asarray(a)).cuda()
+
+
+def make_H(sf, nfft, sr=22050):
+    f = torch.fft.rfftfreq(nfft, d=1 / sr)
+    return f, sf.design_filter(torch.tensor([500.0, 1500.0, 4000.0]), torch.tensor([-10.0, -25.0, -40.0]), f)
+
+
+# --------------------------------------------------------------------------- golden
+@pytest.mark.parametrize("tag", ["n1024", "n4096"])
+def test_golden_forward_and_grads(bu, golden, tag):
+    g = golden(f"operator_{tag}.npz")
+    nfft = int(g["nfft"])
+    x, f, fc, A, H = cuda(g["x"]), cuda(g["f"]), cuda(g["fc"]), cuda(g["A"]), cuda(g["H"])
+    assert rel_l2(bu.design_filter(fc, A, f).cpu(), g["H"]) < TOL
+    assert rel_l2(bu.design_filter(cuda(g["fc_dup"]), cuda(g["A_dup"]), f).cpu(), g["H_dup"]) < TOL
+    assert rel_l2(bu.design_filter(torch.tensor(1000.0).cuda(), torch.tensor(-20.0).cuda(), f).cpu(),
+                  g["H_scalar"]) < TOL
+    assert rel_l2(bu.design_filter([1000.0], [-20.0], f).cpu(), g["H_list"]) < TOL
+    assert rel_l2(bu.design_filter_G(fc, A, torch.tensor(-3.0).cuda(), f).cpu(), g["H_G"]) < TOL
+    X = bu.apply_stft(x, nfft)
+    assert tuple(X.shape) == g["X"].shape
+    assert rel_l2(X.cpu(), g["X"]) < TOL
+    assert rel_l2(bu.apply_filter(x, H, nfft).cpu(), g["y"]) < TOL
+    y2 = bu.apply_filter_istft(cuda(g["X"]), H, nfft)
+    assert tuple(y2.shape) == g["istft"].shape
+    assert rel_l2(y2.cpu(), g["istft"]) < TOL
+    # gradients of <apply_filter(x,H), r> wrt x and H (autograd of the reference)
+    r = cuda(g["r"])
+    xg = x.clone().requires_grad_(True)
+    Hg = H.clone().requires_grad_(True)
+    gx, gH = torch.autograd.grad((bu.apply_filter(xg, Hg, nfft) * r).sum(), (xg, Hg))
+    assert rel_l2(gx.cpu(), g["gx"]) < TOL
+    assert rel_l2(gH.cpu(), g["gH"]) < 5e-5
+    # design_filter VJP
+    fcg, Ag = fc.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    gfc, gA = torch.autograd.grad((bu.design_filter(fcg, Ag, f) * cuda(g["cotH"])).sum(), (fcg, Ag))
+    assert rel_l2(gfc.cpu(), g["gfc"]) < 5e-5
+    assert rel_l2(gA.cpu(), g["gA"]) < 5e-5
+    # rec-guidance operator part through autograd of the drop-in
+    yobs = cuda(g["yobs"])
+    xg = x.clone().requires_grad_(True)
+    nb = torch.linalg.norm(yobs - bu.apply_filter(xg, H, nfft), dim=1, ord=2)
+    (gg,) = torch.autograd.grad(nb.sum(), xg)
+    assert rel_l2(nb.detach().cpu(), g["rg_norms"]) < TOL
+    assert rel_l2(gg.cpu(), g["rg_grad"]) < 2e-5
+
+
+@pytest.mark.parametrize("tag", ["n1024", "n4096"])
+def test_golden_losses(bu, golden, tag):
+    g = golden(f"operator_{tag}.npz")
+    nfft = int(g["nfft"])
+    x, H, yobs = cuda(g["x"]), cuda(g["H"]), cuda(g["yobs"])
+    X, Y = bu.apply_stft(x, nfft), bu.apply_stft(yobs, nfft)
+    for wk in ["linear", "None", "log", "sqrt", "cubic", "quadratic", "logcubic", "logquadratic", "squared"]:
+        for name, val in (("norm_fw_", bu.apply_filter_and_norm_STFTmag_fweighted(X, Y, H, wk)),
+                          ("norm_stft_", bu.apply_norm_STFT_fweighted(yobs, x, wk, nfft)),
+                          ("norm_mag_", bu.apply_norm_STFTmag_fweighted(yobs, x, wk, nfft))):
+            ref = float(g[name + wk])
+            assert abs(float(val) - ref) < 2e-5 * ref, (name, wk)
+    ref = float(g["norm_logmag_sqrt"])
+    assert abs(float(bu.apply_norm_STFTmag_fweighted(yobs, x, "linear", nfft, logmag=True)) - ref) < 1e-4 * ref
+    ref = float(g["norm_plain"])
+    assert abs(float(bu.apply_filter_and_norm_STFTmag(X, Y, H)) - ref) < 2e-5 * ref
+    assert abs(float(bu.apply_norm_filter(H, cuda(g["H_G"]))) - float(g["norm_filter"])) < 1e-6
+    # fit-loss gradients wrt (fc, A) and H exactly as the sampler takes them
+    f = cuda(g["f"])
+    fcg, Ag = cuda(g["fc"]).requires_grad_(True), cuda(g["A"]).requires_grad_(True)
+    Hh = bu.design_filter(fcg, Ag, f)
+    Hh.retain_grad()
+    nrm = bu.apply_filter_and_norm_STFTmag_fweighted(X, Y, Hh, "sqrt")
+    g1, g2, g3 = torch.autograd.grad(nrm, (fcg, Ag, Hh), create_graph=True)
+    assert rel_l2(g3.cpu(), g["fit_gH"]) < 5e-5
+    assert rel_l2(g1.detach().cpu(), g["fit_gfc"]) < 1e-4
+    assert rel_l2(g2.detach().cpu(), g["fit_gA"]) < 1e-4
+
+
+def test_design_filter_index_error(bu):
+    f = torch.fft.rfftfreq(1024, d=1 / 22050).cuda()
+    with pytest.raises(IndexError):
+        bu.design_filter(torch.tensor([100.0, 20000.0]).cuda(), torch.tensor([-5.0, -9.0]).cuda(), f)
+    # fc_0 above the last bin is legal in the reference (H = 1 everywhere)
+    H = bu.design_filter(torch.tensor([20000.0]).cuda(), torch.tensor([-5.0]).cuda(), f)
+    assert torch.equal(H.cpu(), torch.ones(513))
+
+
+# --------------------------------------------------------------------------- oracle, seeded
+@pytest.mark.parametrize("nfft", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 300), (3, 4096), (2, 12289), (5, 40000)])
+def test_apply_filter_vs_oracle(bu, sf, nfft, B, T):
+    torch.manual_seed(nfft + B + T)
+    x = torch.randn(B, T) * 0.063
+    f, H = make_H(sf, nfft)
+    y = bu.apply_filter(x.cuda(), H.cuda(), nfft).cpu()
+    assert y.shape == x.shape
+    assert rel_l2(y, sf.apply_filter(x, H, nfft)) < TOL
+    ya = bu._FilterOp.apply(x.cuda(), H.cuda(), nfft, True).cpu()
+    assert rel_l2(ya, sf.apply_filter_adjoint(x, H, nfft)) < TOL
+
+
+@pytest.mark.parametrize("nfft", [1024, 4096])
+def test_fused_design_and_epilogues(bu, sf, nfft):
+    from babe_b200 import ops
+    torch.manual_seed(5)
+    B, T = 4, 30011
+    x, yobs = torch.randn(B, T) * 0.05, torch.randn(B, T) * 0.05
+    f = torch.fft.rfftfreq(nfft, d=1 / 22050)
+    fc, A = torch.tensor([300.0, 310.0, 900.0, 5000.0]), torch.tensor([-12.0, -14.0, -30.0, -31.0])
+    H = sf.design_filter(fc, A, f)
+    y = ops.apply_filter(x.cuda(), nfft, freqs=f.cuda(), fc=fc.cuda(), A=A.cuda())
+    assert rel_l2(y.cpu(), sf.apply_filter(x, H, nfft)) < TOL
+    ss = torch.zeros(B, dtype=torch.float64, device="cuda")
+    r = ops.apply_filter(x.cuda(), nfft, freqs=f.cuda(), fc=fc.cuda(), A=A.cuda(), sub=yobs.cuda(), row_sumsq=ss)
+    r_ref = sf.apply_filter(x, H, nfft) - yobs
+    assert rel_l2(r.cpu(), r_ref) < TOL
+    assert rel_l2(ss.cpu(), (r_ref.double() ** 2).sum(1)) < TOL
+    n_ref, g_ref = sf.rec_guidance_operator(x, yobs, H, nfft)
+    scale = (1.0 / torch.sqrt(ss)).float()
+    g = ops.apply_filter(r, nfft, freqs=f.cuda(), fc=fc.cuda(), A=A.cuda(), adjoint=True, row_scale=scale)
+    assert rel_l2(torch.sqrt(ss).cpu(), n_ref) < TOL
+    assert rel_l2(g.cpu(), g_ref) < 2e-5
+
+
+@pytest.mark.parametrize("nfft", [512, 1024, 2048, 4096])
+def test_stft_istft_stats_vs_oracle(bu, sf, nfft):
+    from babe_b200 import ops
+    torch.manual_seed(nfft)
+    B, T = 3, 5 * nfft + 77
+    x, y = torch.randn(B, T), torch.randn(B, T) * 0.3
+    f, H = make_H(sf, nfft)
+    X = bu.apply_stft(x.cuda(), nfft)
+    Xo = sf.apply_stft(x, nfft)
+    assert tuple(X.shape) == tuple(Xo.shape)
+    assert rel_l2(X.cpu(), Xo) < TOL
+    assert rel_l2(bu.apply_filter_istft(Xo.cuda(), H.cuda(), nfft).cpu(), sf.apply_filter_istft(Xo, H, nfft)) < TOL
+    abc = ops.stft_stats(x.cuda(), y.cuda(), nfft).cpu()
+    a, b, c = sf.stft_mag_stats(x.double(), y.double(), nfft)
+    assert rel_l2(abc[0], a) < TOL and rel_l2(abc[1], b) < TOL and rel_l2(abc[2], c) < TOL
+    st = ops.spec_mag_stats(X, bu.apply_stft(y.cuda(), nfft)).cpu()
+    assert rel_l2(st[0], a) < TOL and rel_l2(st[1], b) < TOL and rel_l2(st[2], c) < TOL
+    # autograd of the unfused signatures against autograd of the oracle
+    xg = x.clone().requires_grad_(True)
+    cot = torch.randn_like(Xo)
+    (go,) = torch.autograd.grad((sf.apply_stft(xg, nfft) * cot).sum(), xg)
+    xc = x.cuda().requires_grad_(True)
+    (gc,) = torch.autograd.grad((bu.apply_stft(xc, nfft) * cot.cuda()).sum(), xc)
+    assert rel_l2(gc.cpu(), go) < TOL
+    Xg, Hg = Xo.clone().requires_grad_(True), H.clone().requires_grad_(True)
+    yo = sf.apply_filter_istft(Xg, Hg, nfft)
+    cot = torch.randn_like(yo)
+    goX, goH = torch.autograd.grad((yo * cot).sum(), (Xg, Hg))
+    Xc, Hc = Xo.cuda().requires_grad_(True), H.cuda().requires_grad_(True)
+    gcX, gcH = torch.autograd.grad((bu.apply_filter_istft(Xc, Hc, nfft) * cot.cuda()).sum(), (Xc, Hc))
+    # irfft ignores Im of DC/Nyquist; the oracle's autograd agrees
+    assert rel_l2(gcX.cpu(), goX) < TOL
+    assert rel_l2(gcH.cpu(), goH) < 5e-5
+
+
+def test_fit_params_vs_oracle(golden):
+    """Short runs against the reference golden (tight); the full 100 iterations
+    against the fp64 oracle (tight) and the fp32 golden (loose) -- see
+    tests/test_oracle_golden.py::test_fit_params for why."""
+    from babe_b200 import ops, sampler
+    from oracle import filter_fit as ofit, stft_filter as osf
+    g = golden("fit_sampler.npz")
+    nfft, sr = int(g["nfft"]), int(g["sr"])
+    xden, y, p0 = cuda(g["fit_xden"]), cuda(g["y"]), cuda(g["fit_p0"])
+    for iters, tol in ((1, 1e-5), (5, 1e-5), (100, 3e-2)):
+        fit = sampler.FilterFit(nfft=nfft, sample_rate=sr, max_iter=iters, device="cuda")
+        p = fit(xden, y, p0.clone())
+        assert rel_l2(p.cpu(), g[f"fit_p_{iters}"]) < tol, iters
+    cfg = ofit.FitConfig(nfft=nfft, sample_rate=sr)
+    a, b, c = osf.stft_mag_stats(xden.cpu().double(), y.cpu().double(), nfft)
+    s64, it64 = ofit.fit_params_from_stats(a, b, c, p0.cpu().double(), cfg, dtype=torch.float64)
+    fit = sampler.FilterFit(nfft=nfft, sample_rate=sr, max_iter=100, device="cuda")
+    p, iters = fit(xden, y, p0.clone(), return_iters=True)
+    assert int(iters) == it64
+    assert rel_l2(p.cpu(), s64) < 2e-3
+    p7 = fit(xden, y, cuda(g["fit7_p0"]).clone())
+    assert rel_l2(p7.cpu(), g["fit7_p"]) < 3e-2
+
+
+# --------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("B,T,nfft", [(8, 184184, 4096), (2, 485100, 4096), (64, 184184, 4096), (3, 132300, 1024)])
+def test_full_size_properties(bu, sf, B, T, nfft):
+    torch.manual_seed(1)
+    x = torch.randn(B, T, device="cuda") * 0.063
+    g = torch.randn(B, T, device="cuda")
+    f, H = make_H(sf, nfft)
+    H = H.cuda()
+    # identity filter reconstructs x (window / OLA / envelope bookkeeping)
+    assert rel_l2(bu.apply_filter(x, torch.ones_like(H), nfft).cpu(), x.cpu()) < TOL
+    # adjoint identity <A x, g> = <x, A^T g>
+    Ax = bu.apply_filter(x, H, nfft)
+    Atg = bu._FilterOp.apply(g, H, nfft, True)
+    lhs, rhs = (Ax.double() * g.double()).sum(), (x.double() * Atg.double()).sum()
+    assert abs(float(lhs - rhs)) < 1e-5 * abs(float(lhs))
+    # linearity
+    x2 = torch.randn(B, T, device="cuda") * 0.063
+    lin = bu.apply_filter(0.5 * x - 2.0 * x2, H, nfft)
+    assert rel_l2(lin.cpu(), (0.5 * Ax - 2.0 * bu.apply_filter(x2, H, nfft)).cpu()) < TOL
+    # one row against the oracle
+    assert rel_l2(Ax[:1].cpu(), sf.apply_filter(x[:1].cpu(), H.cpu(), nfft)) < TOL
+    # statistics: checksum of checksums (Parseval on the windowed frames)
+    from babe_b200 import ops
+    abc = ops.stft_stats(x, g, nfft).cpu()
+    a1, b1, c1 = sf.stft_mag_stats(x[:1].cpu().double(), g[:1].cpu().double(), nfft)
+    abc1 = ops.stft_stats(x[:1], g[:1], nfft).cpu()
+    assert rel_l2(abc1[0], a1) < TOL and rel_l2(abc1[1], b1) < TOL and rel_l2(abc1[2], c1) < TOL
+    tot = sum(ops.stft_stats(x[i:i + 1], g[i:i + 1], nfft).cpu() for i in range(min(B, 8)))
+    if B <= 8:
+        assert rel_l2(abc, tot) < TOL
