@@ -206,7 +206,11 @@ def test_fit_params_vs_oracle(golden):
     fit = sampler.FilterFit(nfft=nfft, sample_rate=sr, max_iter=100, device="cuda")
     p, iters = fit(xden, y, p0.clone(), return_iters=True)
     assert int(iters) == it64
-    assert rel_l2(p.cpu(), s64) < 2e-3
+    # params are fp32 in the reference and in the kernel: the fp32 trajectory is
+    # pinned by the oracle's fp32 run, the fp64 one only bounds the drift
+    s32, _ = ofit.fit_params_from_stats(a.float(), b.float(), c.float(), p0.cpu(), cfg)
+    assert rel_l2(p.cpu(), s32) < 1e-3
+    assert rel_l2(p.cpu(), s64) < 1e-2
     p7 = fit(xden, y, cuda(g["fit7_p0"]).clone())
     assert rel_l2(p7.cpu(), g["fit7_p"]) < 3e-2
 
