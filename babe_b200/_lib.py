@@ -26,10 +26,23 @@ class FitConfig(ctypes.Structure):
                 ("only_negative_A", c_int)]
 
 
-class CqtGeom(ctypes.Structure):
-    """``babe_cqt_geom`` of include/babe_b200.h."""
-    _fields_ = [("Ls", c_int), ("n1", c_int), ("n2", c_int), ("numocts", c_int),
-                ("binsoct", c_int), ("nbands", c_int), ("coef_per_row", ctypes.c_longlong)]
+MAX_FACTORS = 12
+MAX_OCTAVES = 16
+
+
+class FftFactors(ctypes.Structure):
+    """``babe_fft_factors`` of include/babe_b200.h."""
+    _fields_ = [("n", c_int), ("nf", c_int), ("radix", c_int * MAX_FACTORS)]
+
+
+class CqtPlan(ctypes.Structure):
+    """``babe_cqt_plan`` of include/babe_b200.h (field order matters)."""
+    _fields_ = [("Ls", c_int), ("Nc", c_int), ("f1", FftFactors), ("f2", FftFactors),
+                ("roots1", c_void_p), ("roots2", c_void_p), ("tw_nc", c_void_p), ("tw_ls", c_void_p),
+                ("numocts", c_int), ("binsoct", c_int), ("M", c_int * MAX_OCTAVES),
+                ("fm", FftFactors * MAX_OCTAVES), ("rootsm", c_void_p * MAX_OCTAVES),
+                ("band_p", c_void_p), ("band_lg", c_void_p), ("band_off", c_void_p),
+                ("sum_lg", c_int), ("bin_jlo", c_void_p), ("bin_jhi", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/babe_b200.h declares
@@ -57,6 +70,17 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "babe_fit_params": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                 POINTER(FitConfig), c_void_p, c_void_p]),
+    "babe_cqt_workspace": (c_size_t, [POINTER(CqtPlan), c_int]),
+    "babe_rfft": (c_int, [POINTER(CqtPlan), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                          c_void_p]),
+    "babe_irfft": (c_int, [POINTER(CqtPlan), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                           c_void_p]),
+    "babe_spectral_filter": (c_int, [POINTER(CqtPlan), c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_size_t, c_void_p]),
+    "babe_cqt_analysis": (c_int, [POINTER(CqtPlan), c_void_p, POINTER(c_void_p), c_int, c_void_p,
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "babe_cqt_synthesis": (c_int, [POINTER(CqtPlan), POINTER(c_void_p), c_void_p, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

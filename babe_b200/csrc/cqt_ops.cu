@@ -1,0 +1,583 @@
+// NSGT constant-Q transform kernels for sm_100a.
+//
+// Real FFT of the whole segment (Ls = 184184 = 2^3*7*11*13*23 in the shipped
+// 22.05 kHz configuration -- not a power of two) as a complex FFT of
+// Nc = Ls/2 = n1*n2 points in two passes ("four-step"): every CTA transforms a
+// tile of 8 interleaved sequences entirely in shared memory with a mixed-radix
+// Stockham FFT (smemfft.cuh), so each pass reads and writes the row once with
+// >= 64-byte contiguous segments and the intermediate stays in L2.  The
+// constant-Q filterbank (window multiply, fold, per-band power-of-two iFFT) is
+// one further kernel per direction; overlap-add of the synthesis bands is a
+// deterministic gather (no atomics) fused with the c2r pre-processing.
+//
+// Semantics: oracle/nsgt.py (specification) -- upstream cqt_nsgt_pytorch is not
+// available, see DESIGN.md "CQT parity".  Reference call sites:
+// networks/cqtdiff+.py:620,743,841; testing/blind_bwe_sampler.py:156.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "smemfft.cuh"
+
+namespace babe {
+
+constexpr int CQT_THREADS = 256;
+constexpr int TILE_SEQ = 8;          // sequences per CTA in the two big-FFT passes
+constexpr int TW_LO = 1024;          // low part of the two-level twiddle tables
+
+__device__ __forceinline__ float2 tw2(const float2* tab, int m) {
+  // exp(-2 pi i m / n) = lo[m & 1023] * hi[m >> 10]
+  return cmul(tab[m & (TW_LO - 1)], tab[TW_LO + (m >> 10)]);
+}
+
+static inline int odd_stride(int n) { return n | 1; }
+
+// ---------------------------------------------------------------------------
+// pass 1: for a tile of n2, FFT over n1 (stride n2), twiddle W_Nc^{n2 k1},
+// store as Y[k1][n2]
+// ---------------------------------------------------------------------------
+struct PassArgs {
+  const float2* in; float2* out;
+  int Nc, N1, N2;
+  FftFactors f;
+  const float2* roots;   // n-th roots of this pass
+  const float2* tw_nc;   // two-level W_Nc (pass 1 only)
+  int conj_out;          // pass 2: conjugate on store (inverse transforms)
+};
+
+__global__ void __launch_bounds__(CQT_THREADS) k_fft_cols(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int S = a.N1 | 1;
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  float2* Bf = A + TILE_SEQ * S;
+  float2* roots = Bf + TILE_SEQ * S;
+  float2* tw = roots + a.N1;
+  const int n_hi = (a.Nc >> 10) + 1;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.N1; i += CQT_THREADS) roots[i] = a.roots[i];
+  for (int i = tid; i < TW_LO + n_hi; i += CQT_THREADS) tw[i] = a.tw_nc[i];
+  const int n2_0 = blockIdx.x * TILE_SEQ;
+  const float2* in = a.in + (size_t)blockIdx.y * a.Nc;
+  float2* out = a.out + (size_t)blockIdx.y * a.Nc;
+  for (int idx = tid; idx < TILE_SEQ * a.N1; idx += CQT_THREADS) {
+    const int n2l = idx % TILE_SEQ, n1 = idx / TILE_SEQ;
+    const int n2 = n2_0 + n2l;
+    float2 v = make_float2(0.f, 0.f);
+    if (n2 < a.N2) v = in[(size_t)a.N2 * n1 + n2];
+    A[n2l * S + n1] = v;
+  }
+  __syncthreads();
+  const float2* res = smem_fft(A, Bf, a.f, S, TILE_SEQ, roots, tid, CQT_THREADS);
+  for (int idx = tid; idx < TILE_SEQ * a.N1; idx += CQT_THREADS) {
+    const int n2l = idx % TILE_SEQ, k1 = idx / TILE_SEQ;
+    const int n2 = n2_0 + n2l;
+    if (n2 < a.N2) out[(size_t)k1 * a.N2 + n2] = cmul(res[n2l * S + k1], tw2(tw, n2 * k1));
+  }
+}
+
+// pass 2: for a tile of k1, FFT over n2 (contiguous), store Z[k1 + N1 k2]
+__global__ void __launch_bounds__(CQT_THREADS) k_fft_rows(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int S = a.N2 | 1;
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  float2* Bf = A + TILE_SEQ * S;
+  float2* roots = Bf + TILE_SEQ * S;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.N2; i += CQT_THREADS) roots[i] = a.roots[i];
+  const int k1_0 = blockIdx.x * TILE_SEQ;
+  const float2* in = a.in + (size_t)blockIdx.y * a.Nc;
+  float2* out = a.out + (size_t)blockIdx.y * a.Nc;
+  for (int idx = tid; idx < TILE_SEQ * a.N2; idx += CQT_THREADS) {
+    const int n2 = idx % a.N2, k1l = idx / a.N2;
+    const int k1 = k1_0 + k1l;
+    float2 v = make_float2(0.f, 0.f);
+    if (k1 < a.N1) v = in[(size_t)k1 * a.N2 + n2];
+    A[k1l * S + n2] = v;
+  }
+  __syncthreads();
+  const float2* res = smem_fft(A, Bf, a.f, S, TILE_SEQ, roots, tid, CQT_THREADS);
+  for (int idx = tid; idx < TILE_SEQ * a.N2; idx += CQT_THREADS) {
+    const int k1l = idx % TILE_SEQ, k2 = idx / TILE_SEQ;
+    const int k1 = k1_0 + k1l;
+    if (k1 < a.N1) {
+      float2 v = res[k1l * S + k2];
+      if (a.conj_out) v.y = -v.y;
+      out[(size_t)k1 + (size_t)a.N1 * k2] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// r2c post-processing / c2r pre-processing on bin pairs (k, Nc-k)
+// ---------------------------------------------------------------------------
+// Z = FFT_Nc(x_even + i x_odd)  ->  X[k], X[Nc-k]   (0 < k <= Nc/2)
+__device__ __forceinline__ void post_pair(float2 zk, float2 zkp, float2 W, float2& Xk, float2& Xkp) {
+  const float2 a = zk, b = cconj(zkp);
+  const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+  const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+  const float2 O = make_float2(D.y, -D.x);          // -i D
+  const float2 T = cmul(W, O);
+  Xk = make_float2(E.x + T.x, E.y + T.y);
+  Xkp = make_float2(E.x - T.x, -(E.y - T.y));
+}
+// X[k], X[Nc-k] (Hermitian half spectrum)  ->  conj(Z[k])/Nc, conj(Z[Nc-k])/Nc
+__device__ __forceinline__ void pre_pair(float2 Xk, float2 Xkp, float2 W, float inv_nc,
+                                         float2& Zk, float2& Zkp) {
+  const float2 a = Xk, b = cconj(Xkp);
+  const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
+  const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
+  const float2 O = cmul(cconj(W), D);
+  // Z[k] = E + i O ; Z[kp] = conj(E) + i conj(O); stored conjugated and scaled
+  Zk = make_float2((E.x - O.y) * inv_nc, -(E.y + O.x) * inv_nc);
+  Zkp = make_float2((E.x + O.y) * inv_nc, -(-E.y + O.x) * inv_nc);
+}
+
+__global__ void k_rfft_post(const float2* Z, float2* X, int Nc, const float2* tw_ls,
+                            const float* scale) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > Nc / 2) return;
+  const float2* z = Z + (size_t)blockIdx.y * Nc;
+  float2* x = X + (size_t)blockIdx.y * (Nc + 1);
+  if (k == 0) {
+    const float2 z0 = z[0];
+    const float s0 = scale ? scale[0] : 1.f, sn = scale ? scale[Nc] : 1.f;
+    x[0] = make_float2((z0.x + z0.y) * s0, 0.f);
+    x[Nc] = make_float2((z0.x - z0.y) * sn, 0.f);
+    return;
+  }
+  const int kp = Nc - k;
+  float2 Xk, Xkp;
+  post_pair(z[k], z[kp], tw2(tw_ls, k), Xk, Xkp);
+  if (scale) { const float sk = scale[k], sp = scale[kp]; Xk.x *= sk; Xk.y *= sk; Xkp.x *= sp; Xkp.y *= sp; }
+  x[k] = Xk;
+  if (kp != k) x[kp] = Xkp;
+}
+
+__global__ void k_irfft_pre(const float2* X, float2* Zc, int Nc, const float2* tw_ls,
+                            const float* scale) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > Nc / 2) return;
+  const float2* x = X + (size_t)blockIdx.y * (Nc + 1);
+  float2* z = Zc + (size_t)blockIdx.y * Nc;
+  const int kp = Nc - k;
+  float2 a = x[k], b = x[kp];
+  if (scale) { const float sk = scale[k], sp = scale[kp]; a.x *= sk; a.y *= sk; b.x *= sp; b.y *= sp; }
+  if (k == 0) { a.y = 0.f; b.y = 0.f; }
+  float2 Zk, Zkp;
+  pre_pair(a, b, tw2(tw_ls, k), 1.0f / (float)Nc, Zk, Zkp);
+  z[k] = Zk;
+  if (k != 0 && kp != k) z[kp] = Zkp;
+}
+
+// rfft post * H * irfft pre in one pass (apply_hpf_DC)
+__global__ void k_spectral_mid(const float2* Z, float2* Zc, int Nc, const float2* tw_ls,
+                               const float* H) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > Nc / 2) return;
+  const float2* zi = Z + (size_t)blockIdx.y * Nc;
+  float2* zo = Zc + (size_t)blockIdx.y * Nc;
+  const int kp = Nc - k;
+  const float2 W = tw2(tw_ls, k);
+  float2 Xk, Xkp;
+  if (k == 0) {
+    const float2 z0 = zi[0];
+    Xk = make_float2(z0.x + z0.y, 0.f);
+    Xkp = make_float2(z0.x - z0.y, 0.f);
+  } else {
+    post_pair(zi[k], zi[kp], W, Xk, Xkp);
+  }
+  const float hk = H[k], hp = H[kp];
+  Xk.x *= hk; Xk.y *= hk; Xkp.x *= hp; Xkp.y *= hp;
+  float2 Zk, Zkp;
+  pre_pair(Xk, Xkp, W, 1.0f / (float)Nc, Zk, Zkp);
+  zo[k] = Zk;
+  if (k != 0 && kp != k) zo[kp] = Zkp;
+}
+
+// ---------------------------------------------------------------------------
+// constant-Q bands
+// ---------------------------------------------------------------------------
+struct BandArgs {
+  int Nc, numocts, binsoct, sum_lg;
+  int M[BABE_MAX_OCTAVES];
+  int tb[BABE_MAX_OCTAVES];              // bands per CTA in octave o
+  int tile0[BABE_MAX_OCTAVES + 1];       // first work item of octave o
+  FftFactors fm[BABE_MAX_OCTAVES];
+  const float2* rootsm[BABE_MAX_OCTAVES];
+  float2* coef[BABE_MAX_OCTAVES];        // per-octave coefficient tensors [B, binsoct, M]
+  const int* band_p; const int* band_lg; const int* band_off;
+  const float* win; const float* scale;
+  const float2* X;                       // analysis: half spectrum [B, Nc+1]
+  float2* BS;                            // synthesis: band spectra [B, sum_lg]
+};
+
+__device__ __forceinline__ int find_octave(const BandArgs& a, int item) {
+  int o = 0;
+  while (o + 1 < a.numocts && item >= a.tile0[o + 1]) ++o;
+  return o;
+}
+
+__global__ void __launch_bounds__(CQT_THREADS) k_cqt_analysis(const BandArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int o = find_octave(a, blockIdx.x);
+  const int tile = blockIdx.x - a.tile0[o];
+  const int M = a.M[o], S = M | 1, TB = a.tb[o];
+  const int b0 = tile * TB;
+  const int nb = min(TB, a.binsoct - b0);
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  float2* Bf = A + TB * S;
+  float2* roots = Bf + TB * S;
+  const int tid = threadIdx.x, row = blockIdx.y;
+  for (int i = tid; i < M; i += CQT_THREADS) roots[i] = a.rootsm[o][i];
+  const float2* X = a.X + (size_t)row * (a.Nc + 1);
+  for (int idx = tid; idx < nb * M; idx += CQT_THREADS) {
+    const int bl = idx / M, m = idx - bl * M;
+    const int j = o * a.binsoct + b0 + bl;
+    const int lg = a.band_lg[j], half = lg / 2;
+    // buffer slot m holds window sample i with (i - half) mod M == m
+    int i = m + half;
+    if (i >= M) i -= M;
+    float2 v = make_float2(0.f, 0.f);
+    if (i < lg) {
+      const int k = a.band_p[j] - half + i;
+      if (k >= 0 && k <= a.Nc) {
+        float w = a.win[a.band_off[j] + i];
+        if (a.scale) w *= a.scale[k];
+        const float2 xv = X[k];
+        v = make_float2(xv.x * w, -xv.y * w);      // conjugate: inverse FFT via forward
+      }
+    }
+    A[bl * S + m] = v;
+  }
+  __syncthreads();
+  const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, CQT_THREADS);
+  const float inv_m = 1.0f / (float)M;
+  float2* out = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
+  for (int idx = tid; idx < nb * M; idx += CQT_THREADS) {
+    const int bl = idx / M, m = idx - bl * M;
+    const float2 v = res[bl * S + m];
+    out[(size_t)bl * M + m] = make_float2(v.x * inv_m, -v.y * inv_m);
+  }
+}
+
+__global__ void __launch_bounds__(CQT_THREADS) k_cqt_synth_bands(const BandArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int o = find_octave(a, blockIdx.x);
+  const int tile = blockIdx.x - a.tile0[o];
+  const int M = a.M[o], S = M | 1, TB = a.tb[o];
+  const int b0 = tile * TB;
+  const int nb = min(TB, a.binsoct - b0);
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  float2* Bf = A + TB * S;
+  float2* roots = Bf + TB * S;
+  const int tid = threadIdx.x, row = blockIdx.y;
+  for (int i = tid; i < M; i += CQT_THREADS) roots[i] = a.rootsm[o][i];
+  const float2* in = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
+  for (int idx = tid; idx < nb * M; idx += CQT_THREADS) {
+    const int bl = idx / M, m = idx - bl * M;
+    A[bl * S + m] = in[(size_t)bl * M + m];
+  }
+  __syncthreads();
+  const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, CQT_THREADS);
+  float2* BS = a.BS + (size_t)row * a.sum_lg;
+  for (int idx = tid; idx < nb * M; idx += CQT_THREADS) {
+    const int bl = idx / M, m = idx - bl * M;
+    const int j = o * a.binsoct + b0 + bl;
+    const int lg = a.band_lg[j], half = lg / 2;
+    int i = m + half;
+    if (i >= M) i -= M;
+    if (i < lg) {
+      const float w = a.win[a.band_off[j] + i];
+      const float2 v = res[bl * S + m];
+      BS[a.band_off[j] + i] = make_float2(v.x * w, v.y * w);
+    }
+  }
+}
+
+// overlap-add of the band spectra as a gather, fused with the c2r pre-processing
+struct GatherArgs {
+  const float2* BS; float2* Zc; int Nc, sum_lg;
+  const int* band_p; const int* band_lg; const int* band_off;
+  const int* jlo; const int* jhi;
+  const float* scale; const float2* tw_ls;
+};
+
+__device__ __forceinline__ float2 gather_bin(const GatherArgs& a, const float2* bs, int k) {
+  float2 s = make_float2(0.f, 0.f);
+  const int hi = a.jhi[k];
+  for (int j = a.jlo[k]; j <= hi; ++j) {
+    const int lg = a.band_lg[j];
+    const int i = k - a.band_p[j] + lg / 2;
+    if (i >= 0 && i < lg) {
+      const float2 v = bs[a.band_off[j] + i];
+      s.x += v.x; s.y += v.y;
+    }
+  }
+  if (a.scale) { const float sc = a.scale[k]; s.x *= sc; s.y *= sc; }
+  return s;
+}
+
+__global__ void k_cqt_gather_pre(const GatherArgs a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > a.Nc / 2) return;
+  const float2* bs = a.BS + (size_t)blockIdx.y * a.sum_lg;
+  float2* z = a.Zc + (size_t)blockIdx.y * a.Nc;
+  const int kp = a.Nc - k;
+  float2 Xk = gather_bin(a, bs, k);
+  float2 Xkp = gather_bin(a, bs, kp);
+  if (k == 0) { Xk.y = 0.f; Xkp.y = 0.f; }
+  float2 Zk, Zkp;
+  pre_pair(Xk, Xkp, tw2(a.tw_ls, k), 1.0f / (float)a.Nc, Zk, Zkp);
+  z[k] = Zk;
+  if (k != 0 && kp != k) z[kp] = Zkp;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static inline FftFactors to_dev(const babe_fft_factors& f) {
+  FftFactors d;
+  d.n = f.n; d.nf = f.nf;
+  for (int i = 0; i < MAX_FACTORS; ++i) d.radix[i] = f.radix[i];
+  return d;
+}
+
+static bool radix_ok(int r) {
+  switch (r) { case 2: case 3: case 4: case 5: case 7: case 8: case 11: case 13: case 16:
+    case 17: case 19: case 23: return true; }
+  return false;
+}
+
+static int validate_factors(const babe_fft_factors& f, const char* what) {
+  BABE_REQUIRE(f.n >= 1 && f.nf >= 0 && f.nf <= MAX_FACTORS, BABE_EBADARG, "%s: bad factor list", what);
+  long long p = 1;
+  for (int i = 0; i < f.nf; ++i) {
+    BABE_REQUIRE(radix_ok(f.radix[i]), BABE_EUNSUPPORTED, "%s: unsupported radix %d", what, f.radix[i]);
+    p *= f.radix[i];
+  }
+  BABE_REQUIRE(p == f.n, BABE_EBADARG, "%s: factors multiply to %lld, not %d", what, p, f.n);
+  return BABE_OK;
+}
+
+static int validate_plan(const babe_cqt_plan* p, bool bands) {
+  BABE_REQUIRE(p != nullptr, BABE_EBADARG, "null plan");
+  BABE_REQUIRE(p->Ls >= 4 && p->Ls % 2 == 0 && p->Nc == p->Ls / 2, BABE_EUNSUPPORTED,
+               "signal length %d must be even", p->Ls);
+  int rc = validate_factors(p->f1, "f1");
+  if (rc) return rc;
+  rc = validate_factors(p->f2, "f2");
+  if (rc) return rc;
+  BABE_REQUIRE((long long)p->f1.n * p->f2.n == p->Nc, BABE_EBADARG, "n1*n2 != Nc");
+  BABE_REQUIRE(p->roots1 && p->roots2 && p->tw_nc && p->tw_ls, BABE_EBADARG, "plan tables missing");
+  const size_t smem1 = sizeof(float2) * ((size_t)2 * TILE_SEQ * odd_stride(p->f1.n) + p->f1.n + TW_LO + (p->Nc >> 10) + 1);
+  const size_t smem2 = sizeof(float2) * ((size_t)2 * TILE_SEQ * odd_stride(p->f2.n) + p->f2.n);
+  BABE_REQUIRE(smem1 <= 220 * 1024 && smem2 <= 220 * 1024, BABE_EUNSUPPORTED,
+               "pass lengths %d x %d do not fit shared memory", p->f1.n, p->f2.n);
+  if (bands) {
+    BABE_REQUIRE(p->numocts >= 1 && p->numocts <= BABE_MAX_OCTAVES && p->binsoct >= 1, BABE_EBADARG,
+                 "bad octave layout");
+    BABE_REQUIRE(p->band_p && p->band_lg && p->band_off && p->bin_jlo && p->bin_jhi && p->sum_lg > 0,
+                 BABE_EBADARG, "band tables missing");
+    for (int o = 0; o < p->numocts; ++o) {
+      rc = validate_factors(p->fm[o], "fm");
+      if (rc) return rc;
+      BABE_REQUIRE(p->fm[o].n == p->M[o] && p->rootsm[o] != nullptr, BABE_EBADARG, "octave %d tables", o);
+      BABE_REQUIRE(p->M[o] <= 8192, BABE_EUNSUPPORTED, "octave size %d > 8192", p->M[o]);
+    }
+  }
+  return BABE_OK;
+}
+
+struct Workspace {
+  float2 *bufA, *bufB, *bufX, *bufS;
+};
+
+static size_t ws_bytes(const babe_cqt_plan* p, int B) {
+  return sizeof(float2) * (size_t)B * ((size_t)2 * p->Nc + (p->Nc + 1) + (size_t)std::max(p->sum_lg, 0)) + 256;
+}
+
+static int carve(const babe_cqt_plan* p, int B, void* ws, size_t bytes, Workspace& w) {
+  BABE_REQUIRE(ws != nullptr && bytes >= ws_bytes(p, B), BABE_EBADARG, "workspace too small (%zu < %zu)",
+               bytes, ws_bytes(p, B));
+  w.bufA = static_cast<float2*>(ws);
+  w.bufB = w.bufA + (size_t)B * p->Nc;
+  w.bufX = w.bufB + (size_t)B * p->Nc;
+  w.bufS = w.bufX + (size_t)B * (p->Nc + 1);
+  return BABE_OK;
+}
+
+// complex FFT of B rows of Nc points: in -> tmp (pass 1) -> out (pass 2)
+static int big_fft(const babe_cqt_plan* p, const float2* in, float2* tmp, float2* out, int B,
+                   int conj_out, cudaStream_t st) {
+  PassArgs a{};
+  a.Nc = p->Nc; a.N1 = p->f1.n; a.N2 = p->f2.n;
+  a.tw_nc = reinterpret_cast<const float2*>(p->tw_nc);
+  a.in = in; a.out = tmp; a.f = to_dev(p->f1); a.roots = reinterpret_cast<const float2*>(p->roots1);
+  a.conj_out = 0;
+  const size_t smem1 = sizeof(float2) * ((size_t)2 * TILE_SEQ * odd_stride(a.N1) + a.N1 + TW_LO + (a.Nc >> 10) + 1);
+  cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  k_fft_cols<<<dim3((a.N2 + TILE_SEQ - 1) / TILE_SEQ, B), CQT_THREADS, smem1, st>>>(a);
+  int rc = check_launch("k_fft_cols");
+  if (rc) return rc;
+  a.in = tmp; a.out = out; a.f = to_dev(p->f2); a.roots = reinterpret_cast<const float2*>(p->roots2);
+  a.conj_out = conj_out;
+  const size_t smem2 = sizeof(float2) * ((size_t)2 * TILE_SEQ * odd_stride(a.N2) + a.N2);
+  cudaFuncSetAttribute(k_fft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  k_fft_rows<<<dim3((a.N1 + TILE_SEQ - 1) / TILE_SEQ, B), CQT_THREADS, smem2, st>>>(a);
+  return check_launch("k_fft_rows");
+}
+
+static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int& items) {
+  a.Nc = p->Nc; a.numocts = p->numocts; a.binsoct = p->binsoct; a.sum_lg = p->sum_lg;
+  a.band_p = p->band_p; a.band_lg = p->band_lg; a.band_off = p->band_off;
+  smem = 0;
+  items = 0;
+  for (int o = 0; o < p->numocts; ++o) {
+    const int M = p->M[o];
+    int tb = std::max(1, std::min(p->binsoct, 4096 / M));
+    a.M[o] = M; a.tb[o] = tb; a.tile0[o] = items;
+    a.fm[o] = to_dev(p->fm[o]);
+    a.rootsm[o] = reinterpret_cast<const float2*>(p->rootsm[o]);
+    items += (p->binsoct + tb - 1) / tb;
+    smem = std::max(smem, sizeof(float2) * ((size_t)2 * tb * odd_stride(M) + M));
+  }
+  a.tile0[p->numocts] = items;
+  return BABE_OK;
+}
+
+}  // namespace babe
+
+using namespace babe;
+
+extern "C" size_t babe_cqt_workspace(const babe_cqt_plan* plan, int B) {
+  if (plan == nullptr || B < 1) return 0;
+  return ws_bytes(plan, B);
+}
+
+extern "C" int babe_rfft(const babe_cqt_plan* plan, const float* x, float* X, int B,
+                         const float* bin_scale, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  int rc = validate_plan(plan, false);
+  if (rc) return rc;
+  BABE_REQUIRE(x && X && B >= 1, BABE_EBADARG, "rfft: bad arguments");
+  Workspace w;
+  rc = carve(plan, B, workspace, workspace_bytes, w);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
+  if (rc) return rc;
+  const int n = plan->Nc / 2 + 1;
+  k_rfft_post<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bufB, reinterpret_cast<float2*>(X), plan->Nc,
+                                                        reinterpret_cast<const float2*>(plan->tw_ls),
+                                                        bin_scale);
+  return check_launch("k_rfft_post");
+}
+
+extern "C" int babe_irfft(const babe_cqt_plan* plan, const float* X, float* x, int B,
+                          const float* bin_scale, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  int rc = validate_plan(plan, false);
+  if (rc) return rc;
+  BABE_REQUIRE(x && X && B >= 1, BABE_EBADARG, "irfft: bad arguments");
+  Workspace w;
+  rc = carve(plan, B, workspace, workspace_bytes, w);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = plan->Nc / 2 + 1;
+  k_irfft_pre<<<dim3((n + 255) / 256, B), 256, 0, st>>>(reinterpret_cast<const float2*>(X), w.bufA,
+                                                        plan->Nc,
+                                                        reinterpret_cast<const float2*>(plan->tw_ls),
+                                                        bin_scale);
+  rc = check_launch("k_irfft_pre");
+  if (rc) return rc;
+  return big_fft(plan, w.bufA, w.bufB, reinterpret_cast<float2*>(x), B, 1, st);
+}
+
+extern "C" int babe_spectral_filter(const babe_cqt_plan* plan, const float* x, float* y, int B,
+                                    const float* H, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  int rc = validate_plan(plan, false);
+  if (rc) return rc;
+  BABE_REQUIRE(x && y && H && B >= 1, BABE_EBADARG, "spectral_filter: bad arguments");
+  Workspace w;
+  rc = carve(plan, B, workspace, workspace_bytes, w);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
+  if (rc) return rc;
+  const int n = plan->Nc / 2 + 1;
+  k_spectral_mid<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bufB, w.bufA, plan->Nc,
+                                                           reinterpret_cast<const float2*>(plan->tw_ls), H);
+  rc = check_launch("k_spectral_mid");
+  if (rc) return rc;
+  return big_fft(plan, w.bufA, w.bufB, reinterpret_cast<float2*>(y), B, 1, st);
+}
+
+extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
+                                 float* const* out_octaves_host, int B, const float* win,
+                                 const float* bin_scale, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  int rc = validate_plan(plan, true);
+  if (rc) return rc;
+  BABE_REQUIRE(x && out_octaves_host && win && B >= 1, BABE_EBADARG, "cqt_analysis: bad arguments");
+  Workspace w;
+  rc = carve(plan, B, workspace, workspace_bytes, w);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
+  if (rc) return rc;
+  const int n = plan->Nc / 2 + 1;
+  k_rfft_post<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bufB, w.bufX, plan->Nc,
+                                                        reinterpret_cast<const float2*>(plan->tw_ls),
+                                                        nullptr);
+  rc = check_launch("k_rfft_post");
+  if (rc) return rc;
+  BandArgs a{};
+  size_t smem;
+  int items;
+  fill_band_args(plan, a, smem, items);
+  for (int o = 0; o < plan->numocts; ++o) {
+    BABE_REQUIRE(out_octaves_host[o] != nullptr, BABE_EBADARG, "cqt_analysis: null octave %d", o);
+    a.coef[o] = reinterpret_cast<float2*>(out_octaves_host[o]);
+  }
+  a.win = win; a.scale = bin_scale; a.X = w.bufX;
+  cudaFuncSetAttribute(k_cqt_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_cqt_analysis<<<dim3(items, B), CQT_THREADS, smem, st>>>(a);
+  return check_launch("k_cqt_analysis");
+}
+
+extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const* in_octaves_host,
+                                  float* x, int B, const float* win, const float* bin_scale,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate_plan(plan, true);
+  if (rc) return rc;
+  BABE_REQUIRE(x && in_octaves_host && win && B >= 1, BABE_EBADARG, "cqt_synthesis: bad arguments");
+  Workspace w;
+  rc = carve(plan, B, workspace, workspace_bytes, w);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BandArgs a{};
+  size_t smem;
+  int items;
+  fill_band_args(plan, a, smem, items);
+  for (int o = 0; o < plan->numocts; ++o) {
+    BABE_REQUIRE(in_octaves_host[o] != nullptr, BABE_EBADARG, "cqt_synthesis: null octave %d", o);
+    a.coef[o] = const_cast<float2*>(reinterpret_cast<const float2*>(in_octaves_host[o]));
+  }
+  a.win = win; a.scale = nullptr; a.BS = w.bufS;
+  cudaFuncSetAttribute(k_cqt_synth_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_cqt_synth_bands<<<dim3(items, B), CQT_THREADS, smem, st>>>(a);
+  rc = check_launch("k_cqt_synth_bands");
+  if (rc) return rc;
+  GatherArgs g{};
+  g.BS = w.bufS; g.Zc = w.bufA; g.Nc = plan->Nc; g.sum_lg = plan->sum_lg;
+  g.band_p = plan->band_p; g.band_lg = plan->band_lg; g.band_off = plan->band_off;
+  g.jlo = plan->bin_jlo; g.jhi = plan->bin_jhi; g.scale = bin_scale;
+  g.tw_ls = reinterpret_cast<const float2*>(plan->tw_ls);
+  const int n = plan->Nc / 2 + 1;
+  k_cqt_gather_pre<<<dim3((n + 255) / 256, B), 256, 0, st>>>(g);
+  rc = check_launch("k_cqt_gather_pre");
+  if (rc) return rc;
+  return big_fft(plan, w.bufA, w.bufB, reinterpret_cast<float2*>(x), B, 1, st);
+}

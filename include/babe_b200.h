@@ -136,6 +136,70 @@ int babe_fit_params(const double* abc, const float* w, const float* freqs, int F
                     float* params, int K, const babe_fit_config* cfg_host,
                     int* iters_out, void* stream);
 
+/* ---- a15-a18: NSGT constant-Q transform (cqt_nsgt_pytorch.CQT_nsgt) -------- */
+/* Replaces the third-party class the reference imports at
+ * networks/cqtdiff+.py:9 and calls at :620 (ctor), :743 (fwd), :841 (bwd) and
+ * testing/blind_bwe_sampler.py:156 (apply_hpf_DC).  The plan is a plain
+ * struct filled by the host (babe_b200/cqt.py builds it; any host may): the
+ * length-Ls real FFT is done as a complex FFT of Nc = Ls/2 = n1*n2 points in
+ * two shared-memory passes (four-step), every factor of n1, n2 and of the
+ * octave sizes must be in {2,3,4,5,7,8,11,13,16,17,19,23}. */
+#define BABE_MAX_FACTORS 12
+#define BABE_MAX_OCTAVES 16
+typedef struct {
+  int n;                       /* transform length                       */
+  int nf;                      /* number of stages                       */
+  int radix[BABE_MAX_FACTORS]; /* product == n                           */
+} babe_fft_factors;
+
+typedef struct {
+  int Ls, Nc;                  /* signal length (even), Nc = Ls/2        */
+  babe_fft_factors f1, f2;     /* column pass (n1) and row pass (n2)     */
+  const float* roots1;         /* device float2[n1]  exp(-2 pi i m/n1)   */
+  const float* roots2;         /* device float2[n2]                      */
+  const float* tw_nc;          /* device float2[1024 + Nc/1024 + 1]: exp(-2 pi i m/Nc), m<1024,
+                                  then exp(-2 pi i 1024 m/Nc)            */
+  const float* tw_ls;          /* same two-level table for Ls            */
+  /* constant-Q bands (DC and Nyquist bands excluded) */
+  int numocts, binsoct;
+  int M[BABE_MAX_OCTAVES];     /* coefficients per band in octave o      */
+  babe_fft_factors fm[BABE_MAX_OCTAVES];
+  const float* rootsm[BABE_MAX_OCTAVES]; /* device float2[M_o]           */
+  const int* band_p;           /* device int[nbands]: centre bin         */
+  const int* band_lg;          /* device int[nbands]: window length      */
+  const int* band_off;         /* device int[nbands]: offset into window tables */
+  int sum_lg;                  /* total window samples                   */
+  const int* bin_jlo;          /* device int[Nc+1]: first band covering bin k */
+  const int* bin_jhi;          /* device int[Nc+1]: last band covering bin k (jhi<jlo: none) */
+} babe_cqt_plan;
+
+/* bytes of scratch the calls below need for a batch of B rows */
+size_t babe_cqt_workspace(const babe_cqt_plan* plan, int B);
+
+/* X[B,Nc+1,2] = rfft(x[B,Ls]) * bin_scale (bin_scale[Nc+1] real, optional). */
+int babe_rfft(const babe_cqt_plan* plan, const float* x, float* X, int B, const float* bin_scale,
+              void* workspace, size_t workspace_bytes, void* stream);
+/* x[B,Ls] = irfft(X[B,Nc+1,2] * bin_scale): imaginary parts of the DC and
+ * Nyquist bins are ignored and the 1/Ls normalisation applied, like torch. */
+int babe_irfft(const babe_cqt_plan* plan, const float* X, float* x, int B, const float* bin_scale,
+               void* workspace, size_t workspace_bytes, void* stream);
+/* y = irfft(rfft(x) * H), H[Nc+1] real: CQT_nsgt.apply_hpf_DC (a18) with
+ * H = Hhpf.  Self-adjoint, so it is also its own backward. */
+int babe_spectral_filter(const babe_cqt_plan* plan, const float* x, float* y, int B,
+                         const float* H, void* workspace, size_t workspace_bytes, void* stream);
+/* Analysis (a16 CQT_nsgt.fwd, and the backward of bwd):
+ *   c_j = IFFT_M(fold(rfft(x)[bins of band j] * win[band_off[j]+i] * bin_scale))
+ * out_octaves_host: HOST array of numocts DEVICE pointers, octave o receives
+ * [B, binsoct, M[o]] complex64 (lowest octave first). */
+int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x, float* const* out_octaves_host,
+                      int B, const float* win, const float* bin_scale, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* Synthesis (a17 CQT_nsgt.bwd, and the backward of fwd):
+ *   x = irfft(bin_scale * sum_j unfold(FFT_M(c_j)) * win[band_off[j]+i]) */
+int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const* in_octaves_host, float* x,
+                       int B, const float* win, const float* bin_scale, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

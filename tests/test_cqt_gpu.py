@@ -1,0 +1,109 @@
+"""GPU: the CUDA constant-Q transform against the oracle NSGT (oracle/nsgt.py,
+fp64 on the CPU).  PARITY UNPINNED versus upstream cqt_nsgt_pytorch (not
+available offline); these tests pin the CUDA path to the in-repo specification
+and check the invariants the reference's call sites rely on.  Tolerance:
+relative L2 <= 1e-5 in fp32."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+CONFIGS = [(4, 12, 22050, 8192, 3), (5, 24, 44100, 30030, 2), (7, 64, 22050, 184184, 2),
+           (7, 64, 22050, 132300, 1), (7, 64, 44100, 368368, 1), (8, 96, 44100, 485100, 1)]
+
+
+@pytest.fixture(scope="module")
+def CQT():
+    from babe_b200 import build
+    build.build()
+    from cqt_nsgt_pytorch import CQT_nsgt
+    return CQT_nsgt
+
+
+def _pair(CQT, numocts, binsoct, fs, Ls):
+    from oracle.nsgt import NSGT
+    return (CQT(numocts, binsoct, mode="oct", window=("kaiser", 1), fs=fs, audio_len=Ls, device="cuda"),
+            NSGT(numocts, binsoct, fs, Ls, ("kaiser", 1)))
+
+
+@pytest.mark.parametrize("numocts,binsoct,fs,Ls,B", CONFIGS)
+def test_fft_and_transform_vs_oracle(CQT, numocts, binsoct, fs, Ls, B):
+    cq, ref = _pair(CQT, numocts, binsoct, fs, Ls)
+    assert cq.size_per_oct == ref.M
+    g = torch.Generator().manual_seed(Ls)
+    x = torch.randn(B, Ls, generator=g) * 0.063
+    xc = x.cuda()
+    # the non-power-of-two real FFT itself
+    X = cq.rfft(xc)
+    Xr = torch.fft.rfft(x.double(), dim=-1)
+    assert rel_l2(torch.view_as_real(X.cpu()), torch.view_as_real(Xr)) < TOL
+    assert rel_l2(cq.irfft(Xr.to(torch.complex64).cuda()).cpu(), x) < TOL
+    # analysis
+    c = cq.fwd(xc.unsqueeze(1))
+    cr = ref.fwd(x.double())
+    assert len(c) == numocts
+    for o in range(numocts):
+        assert c[o].shape == (B, 1, binsoct, ref.M[o]) and c[o].dtype == torch.complex64
+        assert rel_l2(torch.view_as_real(c[o].cpu().squeeze(1)), torch.view_as_real(cr[o])) < TOL, o
+    # synthesis from the oracle's coefficients, and the round trip
+    y = cq.bwd([ci.to(torch.complex64).unsqueeze(1).cuda() for ci in cr])
+    assert y.shape == (B, 1, Ls)
+    assert rel_l2(y.cpu().squeeze(1), ref.bwd(cr)) < TOL
+    hp = ref.apply_hpf_DC(x.double())
+    assert rel_l2(cq.bwd(c).cpu().squeeze(1), hp) < TOL
+    assert rel_l2(cq.apply_hpf_DC(xc).cpu(), hp) < TOL
+    assert rel_l2((cq.apply_hpf_DC(xc) + cq.apply_lpf_DC(xc)).cpu(), x) < TOL
+
+
+@pytest.mark.parametrize("numocts,binsoct,fs,Ls,B", CONFIGS[:3])
+def test_gradients_vs_oracle_autograd(CQT, numocts, binsoct, fs, Ls, B):
+    cq, ref = _pair(CQT, numocts, binsoct, fs, Ls)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, Ls, generator=g)
+    cots = [torch.randn(B, binsoct, m, 2, generator=g) for m in ref.M]
+    # d/dx of <fwd(x), cot>
+    xr = x.double().requires_grad_(True)
+    lr = sum((torch.view_as_real(c) * ct.double()).sum() for c, ct in zip(ref.fwd(xr), cots))
+    (gr,) = torch.autograd.grad(lr, xr)
+    xc = x.cuda().requires_grad_(True)
+    lc = sum((torch.view_as_real(c.squeeze(1)) * ct.cuda()).sum() for c, ct in zip(cq.fwd(xc.unsqueeze(1)), cots))
+    (gc,) = torch.autograd.grad(lc, xc)
+    assert rel_l2(gc.cpu(), gr) < TOL
+    # d/dc of <bwd(c), r>
+    r = torch.randn(B, Ls, generator=g)
+    cr = [torch.view_as_complex(ct.double()).requires_grad_(True) for ct in cots]
+    grs = torch.autograd.grad((ref.bwd(cr) * r.double()).sum(), cr)
+    cc = [torch.view_as_complex(ct.contiguous()).unsqueeze(1).cuda().requires_grad_(True) for ct in cots]
+    gcs = torch.autograd.grad((cq.bwd(cc).squeeze(1) * r.cuda()).sum(), cc)
+    for o in range(numocts):
+        assert rel_l2(torch.view_as_real(gcs[o].cpu().squeeze(1)), torch.view_as_real(grs[o])) < TOL, o
+    # hpf is self-adjoint
+    xc = x.cuda().requires_grad_(True)
+    (gh,) = torch.autograd.grad((cq.apply_hpf_DC(xc) * r.cuda()).sum(), xc)
+    assert rel_l2(gh.cpu(), ref.apply_hpf_DC(r.double())) < TOL
+
+
+def test_full_batch_properties(CQT):
+    """Shipped configuration at the benchmark batch: adjoint identities and
+    batch independence (size-independent properties, no CPU oracle run)."""
+    cq = CQT(7, 64, mode="oct", window=("kaiser", 1), fs=22050, audio_len=184184, device="cuda")
+    torch.manual_seed(0)
+    B = 8
+    x = torch.randn(B, 1, 184184, device="cuda") * 0.063
+    c = cq.fwd(x)
+    assert [ci.shape[-1] for ci in c] == [32, 64, 128, 256, 512, 1024, 2048]
+    rec = cq.bwd(c)
+    assert rel_l2(rec.cpu(), cq.apply_hpf_DC(x.squeeze(1)).unsqueeze(1).cpu()) < TOL
+    c1 = cq.fwd(x[3:4])
+    for a, b in zip(c, c1):
+        assert torch.equal(a[3:4], b)
+    cot = [torch.randn_like(torch.view_as_real(ci)) for ci in c]
+    xg = x.clone().requires_grad_(True)
+    loss = sum((torch.view_as_real(ci) * ct).sum() for ci, ct in zip(cq.fwd(xg), cot))
+    (gx,) = torch.autograd.grad(loss, xg)
+    d = torch.randn_like(x)
+    lhs = sum((torch.view_as_real(ci) * ct).double().sum() for ci, ct in zip(cq.fwd(d), cot))
+    assert abs(float(lhs - (gx.double() * d.double()).sum())) < 1e-4 * abs(float(lhs))
