@@ -56,9 +56,11 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p]),
     "babe_design_filter_vjp": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "babe_apply_filter_workspace": (c_size_t, [c_int, c_int, c_int]),
     "babe_apply_filter": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+                                  c_void_p]),
     "babe_stft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                           c_int, c_void_p, c_void_p]),
     "babe_istft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -20,7 +20,7 @@ import math
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, profiling
 from ._lib import BabeError, CqtPlan, FftFactors, check, lib
 
 _RADIX_ORDER = (16, 8, 4, 2, 3, 5, 7, 11, 13, 17, 19, 23)
@@ -173,6 +173,7 @@ class _Plan:
         plan.bin_jlo, plan.bin_jhi = dev(geo.jlo), dev(geo.jhi)
         self.c = plan
         self.n1, self.n2 = n1, n2
+        self.coef_per_row = int(binsoct * sum(geo.M))
         f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
         self.win_g = f32(geo.g)                             # analysis (fwd)
         self.win_gdM = f32(geo.gd * geo.mrep)               # synthesis (bwd)
@@ -217,8 +218,10 @@ def _analysis(plan, x, win, scale):
             for o in range(plan.c.numocts)]
     ptrs = (ctypes.c_void_p * plan.c.numocts)(*[o.data_ptr() for o in outs])
     ws, n = plan.workspace(rows)
-    check(lib().babe_cqt_analysis(ctypes.byref(plan.c), _p(x), ptrs, rows, _p(win), _p(scale),
-                                  _p(ws), n, _stream()), "cqt_analysis")
+    # algorithmic bytes: read x, write the complex coefficients
+    with profiling.op("cqt_analysis", 4, rows * (4 * plan.c.Ls + 8 * plan.coef_per_row)):
+        check(lib().babe_cqt_analysis(ctypes.byref(plan.c), _p(x), ptrs, rows, _p(win), _p(scale),
+                                      _p(ws), n, _stream()), "cqt_analysis")
     return outs
 
 
@@ -228,8 +231,9 @@ def _synthesis(plan, cs, win, scale):
     x = torch.empty((rows, plan.c.Ls), dtype=torch.float32, device=cs[0].device)
     ptrs = (ctypes.c_void_p * plan.c.numocts)(*[c.data_ptr() for c in cs])
     ws, n = plan.workspace(rows)
-    check(lib().babe_cqt_synthesis(ctypes.byref(plan.c), ptrs, _p(x), rows, _p(win), _p(scale),
-                                   _p(ws), n, _stream()), "cqt_synthesis")
+    with profiling.op("cqt_synthesis", 4, rows * (4 * plan.c.Ls + 8 * plan.coef_per_row)):
+        check(lib().babe_cqt_synthesis(ctypes.byref(plan.c), ptrs, _p(x), rows, _p(win), _p(scale),
+                                       _p(ws), n, _stream()), "cqt_synthesis")
     return x
 
 
@@ -237,8 +241,9 @@ def _spectral(plan, x, H):
     rows = x.shape[0]
     y = torch.empty_like(x)
     ws, n = plan.workspace(rows)
-    check(lib().babe_spectral_filter(ctypes.byref(plan.c), _p(x), _p(y), rows, _p(H), _p(ws), n,
-                                     _stream()), "spectral_filter")
+    with profiling.op("spectral_filter", 5, rows * 8 * plan.c.Ls):
+        check(lib().babe_spectral_filter(ctypes.byref(plan.c), _p(x), _p(y), rows, _p(H), _p(ws), n,
+                                         _stream()), "spectral_filter")
     return y
 
 

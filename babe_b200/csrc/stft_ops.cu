@@ -162,7 +162,7 @@ struct FilterArgs {
   const float* window; const float2* twiddle;
   const float* H; const float* freqs; const float* fc; const float* A; int K;
   int adjoint;
-  const float* sub; const float* row_scale; double* row_sumsq;
+  const float* sub; const float* row_scale; double* row_sumsq; double* item_sumsq;
   int* status;
   int bpi;            // output blocks per work item
   int items_per_row;  // ceil(nblk / bpi)
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const Filter
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   __shared__ FilterSegs segs;
+  __shared__ double warp_part[GROUPS][G::TPF / 32];
 
   load_tables(sm, a.window, a.twiddle);
   constexpr float inv_n = 1.0f / G::N;
@@ -284,9 +285,21 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const Filter
       }
       group_sync<G::TPF>(bar);            // ex free for the next pair
     }
-    if (a.row_sumsq != nullptr) {
+    if (a.item_sumsq != nullptr) {
+      // one partial per work item; k_row_sumsq adds them in a fixed order
       acc = warp_sum(acc);
-      if ((threadIdx.x & 31) == 0) atomicAdd(a.row_sumsq + row, acc);
+      if (G::TPF == 32) {
+        if (t == 0) a.item_sumsq[item] = acc;
+      } else {
+        if ((t & 31) == 0) warp_part[grp][t >> 5] = acc;
+        group_sync<G::TPF>(bar);
+        if (t == 0) {
+          double s = 0.0;
+          for (int w = 0; w < G::TPF / 32; ++w) s += warp_part[grp][w];
+          a.item_sumsq[item] = s;
+        }
+        group_sync<G::TPF>(bar);
+      }
     }
   }
 }
@@ -375,6 +388,14 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft_stats(const StatsArg
   __syncthreads();
   float* out = a.partial + ((size_t)blockIdx.x * GROUPS + grp) * 3 * G::F;
   for (int i = t; i < 3 * G::F; i += G::TPF) out[i] = acc[i];
+}
+
+__global__ void k_row_sumsq(const double* item_sumsq, int items_per_row, double* row_sumsq) {
+  // single thread per row: deterministic order, items_per_row is small
+  const int row = blockIdx.x;
+  double s = 0.0;
+  for (int i = 0; i < items_per_row; ++i) s += item_sumsq[(size_t)row * items_per_row + i];
+  row_sumsq[row] += s;
 }
 
 __global__ void k_reduce_stats(const float* partial, int n_partials, int n, double* out) {
@@ -571,7 +592,7 @@ static int pick_chunk(long long rows, int units_per_row, long long capacity, int
 }
 
 template <class G, int GROUPS>
-static int launch_apply_filter(FilterArgs a, cudaStream_t st) {
+static int launch_apply_filter(FilterArgs a, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int hop = G::HOP;
   a.frames = 1 + a.T / hop;
   a.nblk = (a.T - 1) / hop + 1;
@@ -581,10 +602,19 @@ static int launch_apply_filter(FilterArgs a, cudaStream_t st) {
   const long long items = (long long)a.B * a.items_per_row;
   const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
   const size_t smem = Smem<G>::bytes(GROUPS);
+  a.item_sumsq = nullptr;
+  if (a.row_sumsq != nullptr) {
+    BABE_REQUIRE(ws != nullptr && ws_bytes >= (size_t)items * sizeof(double), BABE_EBADARG,
+                 "apply_filter: row_sumsq needs a workspace of babe_apply_filter_workspace() bytes");
+    a.item_sumsq = static_cast<double*>(ws);
+  }
   auto kern = k_apply_filter<G, GROUPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<grid, G::TPF * GROUPS, smem, st>>>(a);
-  return check_launch("k_apply_filter");
+  int rc = check_launch("k_apply_filter");
+  if (rc || a.row_sumsq == nullptr) return rc;
+  k_row_sumsq<<<a.B, 1, 0, st>>>(a.item_sumsq, a.items_per_row, a.row_sumsq);
+  return check_launch("k_row_sumsq");
 }
 
 template <class G, int GROUPS>
@@ -684,8 +714,8 @@ extern "C" int babe_apply_filter(const float* x, float* y, int B, int T, int nff
                                  const float* window, const float* twiddle,
                                  const float* H, const float* freqs, const float* fc,
                                  const float* A, int K, int adjoint, const float* sub,
-                                 const float* row_scale, double* row_sumsq, int* status,
-                                 void* stream) {
+                                 const float* row_scale, double* row_sumsq, void* workspace,
+                                 size_t workspace_bytes, int* status, void* stream) {
   BABE_REQUIRE(x && y && window && twiddle, BABE_EBADARG, "apply_filter: null pointer");
   BABE_REQUIRE(B >= 0 && T >= 0, BABE_EBADARG, "apply_filter: bad shape B=%d T=%d", B, T);
   BABE_REQUIRE(H != nullptr || (freqs && fc && A && K >= 1 && K <= BABE_MAX_BREAKPOINTS),
@@ -699,8 +729,13 @@ extern "C" int babe_apply_filter(const float* x, float* y, int B, int T, int nff
   a.sub = adjoint ? nullptr : sub; a.row_scale = row_scale; a.row_sumsq = row_sumsq;
   a.status = status;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  BABE_DISPATCH_NFFT(nfft, return (launch_apply_filter<G, GR>(a, st)));
+  BABE_DISPATCH_NFFT(nfft, return (launch_apply_filter<G, GR>(a, workspace, workspace_bytes, st)));
   return BABE_EUNSUPPORTED;
+}
+
+extern "C" size_t babe_apply_filter_workspace(int B, int T, int nfft) {
+  if (!babe_stft_supported(nfft) || B < 1 || T < 1) return 0;
+  return (size_t)B * ((T - 1) / (nfft / 2) + 1) * sizeof(double);
 }
 
 extern "C" size_t babe_stft_stats_workspace(int B, int T, int nfft) {

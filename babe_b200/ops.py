@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, profiling
 from ._lib import BabeError, FitConfig, check, lib
 
 _TABLES = {}
@@ -70,8 +70,9 @@ def design_filter(fc, A, freqs, gain_db=None, strict=True):
     g = None if gain_db is None else _cuda_f32(gain_db, "G").reshape(-1)
     H = torch.empty_like(freqs)
     status = torch.zeros(1, dtype=torch.int32, device=freqs.device) if strict else None
-    check(lib().babe_design_filter(_p(fc), _p(A), fc.numel(), _p(g), _p(freqs), freqs.numel(),
-                                   _p(H), _p(status), _stream()), "design_filter")
+    with profiling.op("design_filter", 1, 8 * freqs.numel()):
+        check(lib().babe_design_filter(_p(fc), _p(A), fc.numel(), _p(g), _p(freqs), freqs.numel(),
+                                       _p(H), _p(status), _stream()), "design_filter")
     if strict and int(status.item()) != 0:
         raise IndexError("index 0 is out of bounds for dimension 0 with size 0")
     return H
@@ -86,9 +87,10 @@ def design_filter_vjp(fc, A, freqs, gH, gain_db=None):
     gfc = torch.empty_like(fc)
     gA = torch.empty_like(A)
     gg = torch.empty(1, dtype=torch.float32, device=fc.device) if g is not None else None
-    check(lib().babe_design_filter_vjp(_p(fc), _p(A), fc.numel(), _p(g), _p(freqs), freqs.numel(),
-                                       _p(gH), _p(gfc), _p(gA), _p(gg), _stream()),
-          "design_filter_vjp")
+    with profiling.op("design_filter_vjp", 1, 8 * freqs.numel()):
+        check(lib().babe_design_filter_vjp(_p(fc), _p(A), fc.numel(), _p(g), _p(freqs), freqs.numel(),
+                                           _p(gH), _p(gfc), _p(gA), _p(gg), _stream()),
+              "design_filter_vjp")
     return gfc, gA, gg
 
 
@@ -121,9 +123,16 @@ def apply_filter(x, nfft, H=None, freqs=None, fc=None, A=None, adjoint=False, su
     if row_sumsq is not None and (row_sumsq.dtype != torch.float64 or row_sumsq.numel() != B):
         raise ValueError("row_sumsq must be float64[B]")
     y = torch.empty_like(x) if out is None else out
-    check(lib().babe_apply_filter(_p(x), _p(y), B, T, int(nfft), _p(win), _p(tw), _p(H), _p(freqs),
-                                  _p(fc), _p(A), K, int(bool(adjoint)), _p(sub), _p(row_scale),
-                                  _p(row_sumsq), None, _stream()), "apply_filter")
+    ws, nbytes = None, 0
+    if row_sumsq is not None:
+        nbytes = lib().babe_apply_filter_workspace(B, T, int(nfft))
+        ws = torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
+    # algorithmic bytes: read x, write y (+ read sub)
+    with profiling.op("apply_filter_adj" if adjoint else "apply_filter", 2 if row_sumsq is not None else 1,
+                      (12 if sub is not None else 8) * B * T):
+        check(lib().babe_apply_filter(_p(x), _p(y), B, T, int(nfft), _p(win), _p(tw), _p(H), _p(freqs),
+                                      _p(fc), _p(A), K, int(bool(adjoint)), _p(sub), _p(row_scale),
+                                      _p(row_sumsq), _p(ws), nbytes, None, _stream()), "apply_filter")
     return y
 
 
@@ -135,8 +144,9 @@ def stft(x, nfft, frames=0, in_env_div=False, bin_scale=None):
     if bin_scale is not None:
         bin_scale = _cuda_f32(bin_scale, "bin_scale")
     X = torch.empty(B, nfft // 2 + 1, M, 2, dtype=torch.float32, device=x.device)
-    check(lib().babe_stft(_p(x), _p(X), B, T, int(nfft), int(frames), _p(win), _p(tw),
-                          int(bool(in_env_div)), _p(bin_scale), _stream()), "stft")
+    with profiling.op("stft", 1, 4 * B * T + X.numel() * 4):
+        check(lib().babe_stft(_p(x), _p(X), B, T, int(nfft), int(frames), _p(win), _p(tw),
+                              int(bool(in_env_div)), _p(bin_scale), _stream()), "stft")
     return X
 
 
@@ -151,8 +161,9 @@ def istft(X, nfft, out_len=None, bin_scale=None, out_env_div=True):
     if bin_scale is not None:
         bin_scale = _cuda_f32(bin_scale, "H")
     y = torch.empty(B, out_len, dtype=torch.float32, device=X.device)
-    check(lib().babe_istft(_p(X), _p(y), B, M, int(nfft), int(out_len), _p(win), _p(tw),
-                           _p(bin_scale), int(bool(out_env_div)), _stream()), "istft")
+    with profiling.op("istft", 1, X.numel() * 4 + y.numel() * 4):
+        check(lib().babe_istft(_p(X), _p(y), B, M, int(nfft), int(out_len), _p(win), _p(tw),
+                               _p(bin_scale), int(bool(out_env_div)), _stream()), "istft")
     return y
 
 
@@ -169,8 +180,9 @@ def stft_stats(x, y, nfft, mode=0):
     nbytes = lib().babe_stft_stats_workspace(B, T, int(nfft))
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
     abc = torch.empty(3, F, dtype=torch.float64, device=x.device)
-    check(lib().babe_stft_stats(_p(x), _p(y), B, T, int(nfft), _p(win), _p(tw), int(mode), _p(abc),
-                                _p(ws), nbytes, _stream()), "stft_stats")
+    with profiling.op("stft_stats", 2, 8 * B * T):
+        check(lib().babe_stft_stats(_p(x), _p(y), B, T, int(nfft), _p(win), _p(tw), int(mode), _p(abc),
+                                    _p(ws), nbytes, _stream()), "stft_stats")
     return abc
 
 
@@ -184,8 +196,9 @@ def spec_mag_stats(X, Xref, H=None, w=None):
     H = None if H is None else _cuda_f32(H, "H")
     w = None if w is None else _cuda_f32(w, "w")
     out = torch.empty(4, F, dtype=torch.float64, device=X.device)
-    check(lib().babe_spec_mag_stats(_p(X), _p(Xref), _p(H), _p(w), B, F, M, _p(out), _stream()),
-          "spec_mag_stats")
+    with profiling.op("spec_mag_stats", 1, 2 * X.numel() * 4):
+        check(lib().babe_spec_mag_stats(_p(X), _p(Xref), _p(H), _p(w), B, F, M, _p(out), _stream()),
+              "spec_mag_stats")
     return out
 
 
@@ -202,6 +215,7 @@ def fit_params(abc, w, freqs, params, cfg, return_iters=False):
     F = freqs.numel()
     abc = abc.contiguous()
     iters = torch.zeros(1, dtype=torch.int32, device=params.device) if return_iters else None
-    check(lib().babe_fit_params(_p(abc), _p(w), _p(freqs), F, _p(params), params.shape[1],
-                                ctypes.byref(cfg), _p(iters), _stream()), "fit_params")
+    with profiling.op("fit_params", 1, 3 * F * 8):
+        check(lib().babe_fit_params(_p(abc), _p(w), _p(freqs), F, _p(params), params.shape[1],
+                                    ctypes.byref(cfg), _p(iters), _stream()), "fit_params")
     return (params, iters) if return_iters else params

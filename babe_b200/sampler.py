@@ -97,6 +97,7 @@ class FilterFit:
         self.freqs = torch.fft.rfftfreq(self.nfft, d=1 / sample_rate).to(device)   # :629
         w = bu.freq_weight_vector(freq_weighting, self.nfft // 2 + 1, device)
         self.w = w if w is not None else torch.ones(self.nfft // 2 + 1, device=device)
+        self.joint = False
 
     @classmethod
     def from_args(cls, args, device):
@@ -114,6 +115,9 @@ class FilterFit:
         testing/blind_bwe_sampler.py:577-583) and returned."""
         if abc is None:
             abc = self.stats(x_den, y)
+        if self.joint:                 # one filter for the rows of ALL ranks (SURVEY 8e)
+            from . import distributed
+            distributed.sum_over_ranks_(abc)
         return ops.fit_params(abc, self.w, self.freqs, params, self.cfg, return_iters=return_iters)
 
 
@@ -166,6 +170,8 @@ class BlindSamplerFused:
             self.start_sigma = None
         self.device_noise = device_noise
         self.generator = None          # optional torch.Generator for device noise
+        self.noise_fn = None           # optional callable(shape, device) -> tensor (benchmarks, parity runs)
+        self.joint = False             # True: ranks reproduce ONE reference call on the whole batch
         self._fit = None
 
     def update_diff_params(self):
@@ -176,6 +182,8 @@ class BlindSamplerFused:
 
     # -- noise ---------------------------------------------------------------
     def _randn(self, shape, device):
+        if self.noise_fn is not None:
+            return self.noise_fn(shape, device)
         if self.device_noise:
             return torch.randn(shape, device=device, generator=self.generator)
         return torch.randn(shape).to(device)       # reference: host generator (:513, edm.py:105)
@@ -242,7 +250,12 @@ class BlindSamplerFused:
             else:
                 norm = torch.linalg.norm(y - den_rec, dim=1, ord=ps.norm)
         (rec_grads,) = torch.autograd.grad(outputs=norm.sum(), inputs=x)
-        normguide = torch.linalg.norm(rec_grads) / self.args.exp.audio_len ** 0.5
+        if self.joint:                 # Frobenius norm over the rows of ALL ranks (:125)
+            from . import distributed
+            sq = (rec_grads.double() ** 2).sum().reshape(1)
+            normguide = torch.sqrt(distributed.sum_over_ranks_(sq))[0].float() / self.args.exp.audio_len ** 0.5
+        else:
+            normguide = torch.linalg.norm(rec_grads) / self.args.exp.audio_len ** 0.5
         s = self.xi / (normguide + 1e-6)
         return s * rec_grads / t_i
 
@@ -290,6 +303,7 @@ class BlindSamplerFused:
         device = y.device
         self.freqs = torch.fft.rfftfreq(args.tester.blind_bwe.NFFT, d=1 / args.exp.sample_rate).to(device)
         self._fit = FilterFit.from_args(args, device)
+        self._fit.joint = self.joint
         shape = y.shape
         filter_params = torch.Tensor([args.tester.blind_bwe.initial_conditions.fc,
                                       args.tester.blind_bwe.initial_conditions.A]).to(device)

@@ -75,13 +75,16 @@ int babe_design_filter_vjp(const float* fc, const float* A, int K, const float* 
  * Optional epilogues (any may be NULL):
  *   sub[B,T]       y <- y - sub                       (forward only)
  *   row_scale[B]   y <- y * row_scale[b]
- *   row_sumsq[B]   row_sumsq[b] += sum_t y[b,t]^2     (double, caller zeroes)
+ *   row_sumsq[B]   row_sumsq[b] += sum_t y[b,t]^2     (double, caller zeroes;
+ *                  summed in a fixed order -> bitwise reproducible; needs a
+ *                  workspace of babe_apply_filter_workspace() bytes)
  */
+size_t babe_apply_filter_workspace(int B, int T, int nfft);
 int babe_apply_filter(const float* x, float* y, int B, int T, int nfft,
                       const float* window, const float* twiddle,
                       const float* H, const float* freqs, const float* fc, const float* A, int K,
                       int adjoint, const float* sub, const float* row_scale, double* row_sumsq,
-                      int* status, void* stream);
+                      void* workspace, size_t workspace_bytes, int* status, void* stream);
 
 /* ---- a1: STFT, a2: filter + iSTFT (unfused signatures) ------------------ */
 /* apply_stft (utils/blind_bwe_utils.py:15-26): x[B,T] -> X[B,F,frames,2].
