@@ -147,15 +147,14 @@ class UpDownResample(nn.Module):
         self.pad = len(_CUBIC) // 2 - 1
 
     def forward(self, x):
-        b, c, f, t = x.shape
-        rows = x.reshape(-1, 1, t)
-        w = self.kernel.to(x.dtype)[None, None, :]
+        c = x.shape[1]
+        # depthwise (1 x 8) convolution along time: one FIR per (channel, frequency) row
+        w = self.kernel.to(x.dtype)[None, None, None, :].expand(c, 1, 1, -1)
         if self.down:
-            out = F.conv1d(F.pad(rows, (self.pad,) * 2, 'reflect'), w, stride=2)
-        else:
-            out = F.conv_transpose1d(F.pad(rows, ((self.pad + 1) // 2,) * 2, 'reflect'), w, stride=2,
-                                     padding=self.pad * 2 + 1)
-        return out.reshape(b, c, f, out.shape[-1])
+            return F.conv2d(F.pad(x, (self.pad, self.pad, 0, 0), 'reflect'), w, stride=(1, 2), groups=c)
+        p = (self.pad + 1) // 2
+        return F.conv_transpose2d(F.pad(x, (p, p, 0, 0), 'reflect'), w, stride=(1, 2),
+                                  padding=(0, self.pad * 2 + 1), groups=c)
 
 
 class CQTDiffPlus(nn.Module):

@@ -59,6 +59,9 @@ def test_rid_outputs_and_device_noise(golden):
     x, p, den, t, filt = out
     assert den.shape == (4, *y.shape) and filt.shape == (4, 2, 5) and t.shape == (5,)
     assert torch.isfinite(x).all()
+    # every babe_b200 kernel is bitwise reproducible (fixed-order reductions, no
+    # atomics); cuDNN's conv backward in the toy denoiser needs its deterministic mode
+    torch.backends.cudnn.deterministic = True
     s.device_noise = True
     s.generator = torch.Generator(device="cuda").manual_seed(3)
     x1, _ = s.predict_blind_bwe(y.clone())
