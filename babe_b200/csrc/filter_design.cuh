@@ -61,6 +61,38 @@ __device__ inline void build_segments(FilterSegs& s, const float* fc, const floa
   }
 }
 
+// CTA-cooperative variant: K threads search their breakpoint in parallel (the
+// binary searches are chains of dependent global loads), thread 0 then links the
+// anchors from registers/shared memory only.  Contains two CTA barriers.
+__device__ inline void build_segments_coop(FilterSegs& s, float* fkf /*shared, K floats*/,
+                                           const float* fc, const float* A, int K, const float* f,
+                                           int F) {
+  const int i = threadIdx.x;
+  if (i < K) {
+    const float c = fc[i];
+    s.fc[i] = c;
+    s.A[i] = A[i];
+    const int k = first_bin_ge(f, F, c);
+    s.kf[i] = k;
+    fkf[i] = (k < F) ? f[k] : 0.f;
+  }
+  __syncthreads();
+  if (i == 0) {
+    s.K = K;
+    s.bad = 0;
+    for (int a = 0; a < K; ++a) {
+      int p = -1;
+      for (int j = 0; j < a; ++j)
+        if (s.kf[j] <= s.kf[a]) p = j;
+      s.parent[a] = p;
+      if (a > 0 && s.kf[a] >= F) { s.bad = 1; s.anchor[a] = 1.0f; continue; }
+      s.anchor[a] = (a == 0 || p < 0) ? 1.0f
+                                      : __fmul_rn(seg_gain(s.A[p], s.fc[p], fkf[a]), s.anchor[p]);
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ int bin_owner(const FilterSegs& s, int k) {
   int o = -1;
 #pragma unroll 4

@@ -20,11 +20,9 @@ constexpr int FIT_WARPS = FIT_THREADS / 32;
 __global__ void k_design_filter(const float* fc, const float* A, int K, const float* gain_db,
                                 const float* freqs, int F, float* H, int* status) {
   __shared__ FilterSegs segs;
-  if (threadIdx.x == 0) {
-    build_segments(segs, fc, A, K, freqs, F);
-    if (segs.bad && status != nullptr && blockIdx.x == 0) *status = 1;
-  }
-  __syncthreads();
+  __shared__ float fkf[BABE_MAX_BREAKPOINTS];
+  build_segments_coop(segs, fkf, fc, A, K, freqs, F);
+  if (threadIdx.x == 0 && segs.bad && status != nullptr && blockIdx.x == 0) *status = 1;
   float g = 1.0f;
   if (gain_db != nullptr) g = exp10f(__fdiv_rn(gain_db[0], 20.0f));
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < F; k += gridDim.x * blockDim.x) {
@@ -88,8 +86,8 @@ k_design_filter_vjp(const float* fc, const float* A, int K, const float* gain_db
                     float* ggain_out) {
   __shared__ FilterSegs segs;
   __shared__ double scratch[FIT_WARPS * (2 * KMAX + 1)];
-  if (threadIdx.x == 0) build_segments(segs, fc, A, K, freqs, F);
-  __syncthreads();
+  __shared__ float fkf[BABE_MAX_BREAKPOINTS];
+  build_segments_coop(segs, fkf, fc, A, K, freqs, F);
   float g = 1.0f;
   if (gain_db != nullptr) g = exp10f(__fdiv_rn(gain_db[0], 20.0f));
   double v[2 * KMAX + 1];
@@ -127,30 +125,48 @@ struct FitArgs {
 };
 
 __global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) {
+  // Per iteration: (1) K threads locate their breakpoints, thread 0 links the
+  // anchors; (2) every thread evaluates its bins: H_k, the loss term and
+  // u_k = (norm dnorm/dH_k) H_k, into shared memory; (3) warp i sums u and
+  // u*log2(f/fc_i) over the bins segment i owns, one more warp sums the loss;
+  // (4) thread 0 applies the chain rule through the anchors, the fp32 gradient
+  // step, the sequential clamps and the stopping test.  All sums run in a fixed
+  // order (bitwise reproducible).
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int F = a.F, K = a.K;
   double* sa = reinterpret_cast<double*>(smem_raw);            // w^2 a
-  double* sb = sa + a.F;                                       // w^2 b
-  float* sf = reinterpret_cast<float*>(sb + a.F);              // freqs
+  double* sb = sa + F;                                         // w^2 b
+  double* su = sb + F;                                         // u_k
+  double* sl = su + F;                                         // u_k log2(f_k/fc_owner)
+  double* ss = sl + F;                                         // loss term
+  float* sf = reinterpret_cast<float*>(ss + F);                // freqs
+  signed char* sown = reinterpret_cast<signed char*>(sf + F);  // owner of bin k
   __shared__ FilterSegs segs;
-  __shared__ double scratch[FIT_WARPS * (2 * KMAX + 1)];
+  __shared__ float fkf[KMAX];
+  __shared__ double scratch[FIT_WARPS];
+  __shared__ double red[2 * KMAX + 1];
   __shared__ float cur[2 * KMAX], prev[2 * KMAX];
   __shared__ int stop_flag;
   __shared__ double c_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  const int F = a.F, K = a.K;
   {
-    double v[1] = {0.0};
+    double v = 0.0;
     for (int k = threadIdx.x; k < F; k += blockDim.x) {
       const double w2 = (double)a.w[k] * (double)a.w[k];
       sa[k] = w2 * a.abc[k];
       sb[k] = w2 * a.abc[F + k];
       sf[k] = a.freqs[k];
-      v[0] += w2 * a.abc[2 * F + k];
+      v += w2 * a.abc[2 * F + k];
     }
-    block_sum<1>(v, scratch);
+    v = warp_sum(v);
+    if (lane == 0) scratch[warp] = v;
+    if (threadIdx.x < K) { cur[threadIdx.x] = a.params[threadIdx.x]; cur[KMAX + threadIdx.x] = a.params[K + threadIdx.x]; }
+    __syncthreads();
     if (threadIdx.x == 0) {
-      c_total = v[0];
-      for (int i = 0; i < K; ++i) { cur[i] = a.params[i]; cur[KMAX + i] = a.params[K + i]; }
+      double s = 0.0;
+      for (int w = 0; w < FIT_WARPS; ++w) s += scratch[w];
+      c_total = s;
       stop_flag = 0;
     }
   }
@@ -158,31 +174,39 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) 
 
   int it = 0;
   for (int iter = 0; iter < a.cfg.max_iter; ++iter) {
-    if (threadIdx.x == 0) build_segments(segs, cur, cur + KMAX, K, sf, F);
-    __syncthreads();
-    double v[2 * KMAX + 1];
-#pragma unroll
-    for (int i = 0; i < 2 * KMAX + 1; ++i) v[i] = 0.0;
-    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+    build_segments_coop(segs, fkf, cur, cur + KMAX, K, sf, F);          // (1)
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {                 // (2)
       const float fk = sf[k];
       const int o = bin_owner(segs, k);
       const double h = (double)bin_gain(segs, k, fk);
       const double wa = sa[k], wb = sb[k];
-      v[2 * KMAX] += h * (h * wa - 2.0 * wb);            // S without the c term
+      ss[k] = h * (h * wa - 2.0 * wb);
+      double u = 0.0, l = 0.0;
       if (o >= 0) {
-        const double u = (h * wa - wb) * h;              // (norm * dnorm/dH_k) * H_k
-        const double lg = (double)log2f(__fdiv_rn(fk, segs.fc[o]));
-#pragma unroll
-        for (int i = 0; i < KMAX; ++i) {
-          if (i == o) { v[i] += u; v[KMAX + i] += u * lg; }
-        }
+        u = (h * wa - wb) * h;
+        l = u * (double)log2f(__fdiv_rn(fk, segs.fc[o]));
+      }
+      su[k] = u; sl[k] = l; sown[k] = (signed char)o;
+    }
+    __syncthreads();
+    for (int q = warp; q <= K; q += FIT_WARPS) {                        // (3)
+      double s0 = 0.0, s1 = 0.0;
+      if (q < K) {
+        for (int k = lane; k < F; k += 32)
+          if (sown[k] == q) { s0 += su[k]; s1 += sl[k]; }
+      } else {
+        for (int k = lane; k < F; k += 32) s0 += ss[k];
+      }
+      s0 = warp_sum(s0); s1 = warp_sum(s1);
+      if (lane == 0) {
+        if (q < K) { red[q] = s0; red[KMAX + q] = s1; } else { red[2 * KMAX] = s0; }
       }
     }
-    block_sum<2 * KMAX + 1>(v, scratch);
-    if (threadIdx.x == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {                                             // (4)
       double gfc[KMAX], gA[KMAX];
-      finish_param_grads(segs, sf, F, v, v + KMAX, gfc, gA);
-      const double S = v[2 * KMAX] + c_total;
+      finish_param_grads(segs, sf, F, red, red + KMAX, gfc, gA);
+      const double S = red[2 * KMAX] + c_total;
       const double inv_norm = 1.0 / sqrt(S > 0.0 ? S : 0.0);
       // gradient step in fp32 like the reference (:569), then the clamps (:576-583)
       for (int i = 0; i < K; ++i) {
@@ -290,7 +314,7 @@ extern "C" int babe_fit_params(const double* abc, const float* w, const float* f
                                int* iters_out, void* stream) {
   BABE_REQUIRE(abc && w && freqs && params && cfg, BABE_EBADARG, "fit_params: null pointer");
   BABE_REQUIRE(K >= 1 && K <= KMAX, BABE_EBADARG, "fit_params: K=%d outside [1,%d]", K, KMAX);
-  const size_t smem = (size_t)F * (2 * sizeof(double) + sizeof(float));
+  const size_t smem = (size_t)F * (5 * sizeof(double) + sizeof(float) + 1) + 16;
   BABE_REQUIRE(F >= 1 && smem <= 200 * 1024, BABE_EUNSUPPORTED, "fit_params: F=%d too large", F);
   FitArgs a{abc, w, freqs, F, params, K, *cfg, iters_out};
   cudaFuncSetAttribute(k_fit_params, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,20 +1,30 @@
 // STFT-domain operator kernels for sm_100a.
 //
-// All kernels share one transform core: a length-N complex FFT (N = R1*R2,
-// R in {16,32,64}) computed in two in-register passes by max(R1,R2) threads
-// (a "frame group"), with one shared-memory transposition between the passes.
-// Two real frames are carried through each complex transform (frame A in the
-// real part, frame B in the imaginary part).  Because the lowpass response H
-// is real and symmetric the packed spectrum can be multiplied by H directly
-// and inverted without ever separating the two frames, so the fused
-// STFT -> H -> iSTFT operator costs one forward and one inverse complex FFT
-// per PAIR of frames, the window, overlap-add and envelope division happen in
-// registers, and x is read and y written exactly once.
+// All kernels share one transform core: a length-N complex FFT computed by a
+// "frame group" of threads in two or three in-register passes with
+// shared-memory transpositions in between.  Two real frames are carried through
+// each complex transform (frame A in the real part, frame B in the imaginary
+// part).  Because the lowpass response H is real and symmetric the packed
+// spectrum can be multiplied by H directly and inverted without ever
+// separating the two frames, so the fused STFT -> H -> iSTFT operator costs one
+// forward and one inverse complex FFT per PAIR of frames; window, overlap-add
+// and envelope division happen in registers, x is read and y written once.
+//
+//   Core3 (N = 4096 = 16*16*16): 256 threads per frame pair, 16 points per
+//     thread, three radix-16 passes.  ~100 registers/thread -> two 256-thread
+//     CTAs per SM (16 warps) and a code footprint that fits the instruction
+//     cache.  (Round-1 profile of the earlier 64x64 two-pass core: 255
+//     registers, 8 warps/SM, long-scoreboard + no-instruction stalls, 4 % of HBM
+//     peak -- profiles/r01_apply_filter_64x64.md.)
+//   Core2<R1,R2> (N = R1*R2, R in {16,32,64}): two passes, max(R1,R2) threads
+//     per frame pair; used for NFFT 512/1024/2048.
 //
 // Reference semantics: utils/blind_bwe_utils.py:6-39 of eloimoliner/BABE
 // (periodic Hamming window, hop N/2, right zero padding by N, center=False,
 // torch.istft envelope normalisation).
 #include <math.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "filter_design.cuh"
@@ -22,99 +32,201 @@
 
 namespace babe {
 
+__device__ __forceinline__ float2 cmulf(float ar, float ai, float2 w) {
+  return make_float2(ar * w.x - ai * w.y, ar * w.y + ai * w.x);
+}
+__device__ __forceinline__ float2 cmulcf(float ar, float ai, float2 w) {   // * conj(w)
+  return make_float2(ar * w.x + ai * w.y, ai * w.x - ar * w.y);
+}
+
+// ---------------------------------------------------------------------------
+// Core interface (all static):
+//   N, HOP, F, TPF                      threads per frame group
+//   NT, TS, TT   time role : thread t < TT holds z[TS*i + t], i < NT
+//   NF, KS, FT   freq role : thread t < FT holds Z[t + KS*i], i < NF
+//   EX_ELEMS, TW_SMEM                   float2 elements of exchange / twiddle smem
+//   Regs, init_regs()                   per-thread twiddle constants
+//   load_twiddles()                     fill the shared twiddle table (CTA-wide)
+//   fwd(), inv(), mirror()
+// `roots` is the table exp(-2 pi i m / N), m < N.
+// Callers must pass a group barrier between two uses of `ex` (fwd/inv/mirror
+// each end with reads of ex by other threads' data).
+// ---------------------------------------------------------------------------
 template <int R1_, int R2_>
-struct Geo {
+struct Core2 {
   static constexpr int R1 = R1_, R2 = R2_;
   static constexpr int N = R1 * R2, HOP = N / 2, F = N / 2 + 1;
-  static constexpr int TPF = R1 > R2 ? R1 : R2;            // threads per frame group
+  static constexpr int TPF = R1 > R2 ? R1 : R2;
+  static constexpr int NT = R1, TS = R2, TT = R2;
+  static constexpr int NF = R2, KS = R1, FT = R1;
   static constexpr int EXF = R2 + 1;                        // forward exchange  [k1][n2]
   static constexpr int EXI = R1 + 1;                        // inverse exchange  [n2][k1]
   static constexpr int EX_ELEMS = (R1 * EXF > R2 * EXI) ? R1 * EXF : R2 * EXI;
-  static constexpr int TW_ELEMS = R1 * EXF;                 // padded twiddle table [k1][n2]
+  static constexpr int TW_SMEM = R1 * EXF;                  // padded twiddle table [k1][n2]
+  struct Regs {};
+  __device__ static __forceinline__ void init_regs(Regs&, const float2*, int) {}
+  __device__ static __forceinline__ void load_twiddles(float2* tw, const float2* roots) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const int k1 = i / R2, n2 = i % R2;
+      tw[k1 * EXF + n2] = roots[k1 * n2];
+    }
+  }
+  __device__ static __forceinline__ void fwd(float (&ar)[NT], float (&ai)[NT], float (&br)[NF],
+                                             float (&bi)[NF], float2* ex, const float2* tw,
+                                             const Regs&, int t, int bar) {
+    if (t < TT) {
+      fft_reg<R1>(ar, ai);
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) ex[k1 * EXF + t] = cmulf(ar[k1], ai[k1], tw[k1 * EXF + t]);
+    }
+    group_sync<TPF>(bar);
+    if (t < FT) {
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) {
+        const float2 v = ex[t * EXF + n2];
+        br[n2] = v.x; bi[n2] = v.y;
+      }
+      fft_reg<R2>(br, bi);
+    }
+  }
+  // in : Z[t + R1*k2]; out: N * z[R2*n1 + t] (unnormalised)
+  __device__ static __forceinline__ void inv(float (&br)[NF], float (&bi)[NF], float (&ar)[NT],
+                                             float (&ai)[NT], float2* ex, const float2* tw,
+                                             const Regs&, int t, int bar) {
+    if (t < FT) {
+      fft_reg<R2>(bi, br);
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) ex[n2 * EXI + t] = cmulcf(br[n2], bi[n2], tw[t * EXF + n2]);
+    }
+    group_sync<TPF>(bar);
+    if (t < TT) {
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) {
+        const float2 v = ex[t * EXI + k1];
+        ar[k1] = v.x; ai[k1] = v.y;
+      }
+      fft_reg<R1>(ai, ar);
+    }
+  }
+  // (pr,pi)[k2] <- Z[N - (t + R1*k2)]
+  __device__ static __forceinline__ void mirror(const float (&br)[NF], const float (&bi)[NF],
+                                                float (&pr)[NF], float (&pi)[NF], float2* ex, int t,
+                                                int bar) {
+    if (t < FT) {
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) ex[t * EXF + k2] = make_float2(br[k2], bi[k2]);
+    }
+    group_sync<TPF>(bar);
+    if (t < FT) {
+      const int pt = (R1 - t) % R1;
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) {
+        const int pk = (t == 0) ? ((R2 - k2) % R2) : (R2 - 1 - k2);
+        const float2 v = ex[pt * EXF + pk];
+        pr[k2] = v.x; pi[k2] = v.y;
+      }
+    }
+  }
 };
 
-// ---------------------------------------------------------------------------
-// transform core
-// ---------------------------------------------------------------------------
-// in : thread t < R2 holds z[R2*n1 + t] in (ar,ai)[n1], n1 < R1
-// out: thread t < R1 holds Z[t + R1*k2] in (br,bi)[k2], k2 < R2
-template <class G>
-__device__ __forceinline__ void fwd_pair(float (&ar)[G::R1], float (&ai)[G::R1],
-                                         float (&br)[G::R2], float (&bi)[G::R2],
-                                         float2* ex, const float2* tw, int t, int bar) {
-  if (t < G::R2) {
-    fft_reg<G::R1>(ar, ai);
+// N = 4096 = 16 * 16 * 16.  n = 256 n1 + 16 n2 + n3, k = k1 + 16 k2 + 256 k3.
+//   P1: thread (n2,n3) = t         FFT over n1 -> k1, * W_4096^{t k1}   -> ex[k1][t]
+//   P2: thread (k1 = t/16, n3)     FFT over n2 -> k2, in place in ex
+//   P3: thread (k1 = t%16, k2)     * W_256^{n3 k2}, FFT over n3 -> k3   => Z[t + 256 k3]
+// ex rows are padded to 257 float2 so that all three access patterns are
+// bank-conflict free.  The inverse runs the same passes backwards.
+struct Core3 {
+  static constexpr int N = 4096, HOP = 2048, F = 2049;
+  static constexpr int TPF = 256;
+  static constexpr int NT = 16, TS = 256, TT = 256;
+  static constexpr int NF = 16, KS = 256, FT = 256;
+  static constexpr int ROW = 257;
+  static constexpr int EX_ELEMS = 16 * ROW;
+  static constexpr int TW_SMEM = 256;                       // W_256^m
+  struct Regs { float wr[16], wi[16]; };                    // W_4096^{t k1}
+  __device__ static __forceinline__ void init_regs(Regs& r, const float2* roots, int t) {
 #pragma unroll
-    for (int k1 = 0; k1 < G::R1; ++k1) {
-      const float2 w = tw[k1 * G::EXF + t];
-      float2 v;
-      v.x = ar[k1] * w.x - ai[k1] * w.y;
-      v.y = ar[k1] * w.y + ai[k1] * w.x;
-      ex[k1 * G::EXF + t] = v;
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const float2 w = roots[t * k1];
+      r.wr[k1] = w.x; r.wi[k1] = w.y;
     }
   }
-  group_sync<G::TPF>(bar);
-  if (t < G::R1) {
+  __device__ static __forceinline__ void load_twiddles(float2* tw, const float2* roots) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tw[i] = roots[16 * i];
+  }
+  __device__ static __forceinline__ void fwd(float (&ar)[16], float (&ai)[16], float (&br)[16],
+                                             float (&bi)[16], float2* ex, const float2* tw,
+                                             const Regs& rg, int t, int bar) {
+    fft_reg<16>(ar, ai);
 #pragma unroll
-    for (int n2 = 0; n2 < G::R2; ++n2) {
-      const float2 v = ex[t * G::EXF + n2];
-      br[n2] = v.x; bi[n2] = v.y;
+    for (int k1 = 0; k1 < 16; ++k1)
+      ex[k1 * ROW + t] = make_float2(ar[k1] * rg.wr[k1] - ai[k1] * rg.wi[k1],
+                                     ar[k1] * rg.wi[k1] + ai[k1] * rg.wr[k1]);
+    group_sync<TPF>(bar);
+    {
+      float2* col = ex + (t >> 4) * ROW + (t & 15);          // + 16 n2
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) { const float2 v = col[16 * n2]; br[n2] = v.x; bi[n2] = v.y; }
+      fft_reg<16>(br, bi);
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) col[16 * k2] = make_float2(br[k2], bi[k2]);
     }
-    fft_reg<G::R2>(br, bi);
-  }
-}
-
-// in : thread t < R1 holds Z[t + R1*k2] in (br,bi)[k2]
-// out: thread t < R2 holds N * z[R2*n1 + t] in (ar,ai)[n1]  (unnormalised)
-// The caller must have passed a group barrier since the last read of `ex`.
-template <class G>
-__device__ __forceinline__ void inv_pair(float (&br)[G::R2], float (&bi)[G::R2],
-                                         float (&ar)[G::R1], float (&ai)[G::R1],
-                                         float2* ex, const float2* tw, int t, int bar) {
-  if (t < G::R1) {
-    fft_reg<G::R2>(bi, br);   // inverse over k2 -> n2
+    group_sync<TPF>(bar);
+    {
+      const int k2 = t >> 4;
+      const float2* row = ex + (t & 15) * ROW + 16 * k2;      // + n3
 #pragma unroll
-    for (int n2 = 0; n2 < G::R2; ++n2) {
-      const float2 w = tw[t * G::EXF + n2];          // conj(w) below
-      float2 v;
-      v.x = br[n2] * w.x + bi[n2] * w.y;
-      v.y = bi[n2] * w.x - br[n2] * w.y;
-      ex[n2 * G::EXI + t] = v;
-    }
-  }
-  group_sync<G::TPF>(bar);
-  if (t < G::R2) {
-#pragma unroll
-    for (int k1 = 0; k1 < G::R1; ++k1) {
-      const float2 v = ex[t * G::EXI + k1];
-      ar[k1] = v.x; ai[k1] = v.y;
-    }
-    fft_reg<G::R1>(ai, ar);   // inverse over k1 -> n1
-  }
-}
-
-// Exchange so that thread t < R1 additionally sees P[k2] = Z[N - (t + R1*k2)].
-// On return (pr,pi)[k2] holds that partner value.  Needs a barrier before
-// (ex free) and leaves ex busy until the next barrier.
-template <class G>
-__device__ __forceinline__ void mirror_exchange(const float (&br)[G::R2], const float (&bi)[G::R2],
-                                                float (&pr)[G::R2], float (&pi)[G::R2],
-                                                float2* ex, int t, int bar) {
-  if (t < G::R1) {
-#pragma unroll
-    for (int k2 = 0; k2 < G::R2; ++k2) ex[t * G::EXF + k2] = make_float2(br[k2], bi[k2]);
-  }
-  group_sync<G::TPF>(bar);
-  if (t < G::R1) {
-    const int pt = (G::R1 - t) % G::R1;
-#pragma unroll
-    for (int k2 = 0; k2 < G::R2; ++k2) {
-      const int pk = (t == 0) ? ((G::R2 - k2) % G::R2) : (G::R2 - 1 - k2);
-      const float2 v = ex[pt * G::EXF + pk];
-      pr[k2] = v.x; pi[k2] = v.y;
+      for (int n3 = 0; n3 < 16; ++n3) {
+        const float2 v = cmulf(row[n3].x, row[n3].y, tw[n3 * k2]);
+        br[n3] = v.x; bi[n3] = v.y;
+      }
+      fft_reg<16>(br, bi);
     }
   }
-}
+  __device__ static __forceinline__ void inv(float (&br)[16], float (&bi)[16], float (&ar)[16],
+                                             float (&ai)[16], float2* ex, const float2* tw,
+                                             const Regs& rg, int t, int bar) {
+    {
+      const int k2 = t >> 4;
+      float2* row = ex + (t & 15) * ROW + 16 * k2;
+      fft_reg<16>(bi, br);                                    // inverse over k3 -> n3
+#pragma unroll
+      for (int n3 = 0; n3 < 16; ++n3) row[n3] = cmulcf(br[n3], bi[n3], tw[n3 * k2]);
+    }
+    group_sync<TPF>(bar);
+    {
+      float2* col = ex + (t >> 4) * ROW + (t & 15);
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) { const float2 v = col[16 * k2]; br[k2] = v.x; bi[k2] = v.y; }
+      fft_reg<16>(bi, br);                                    // inverse over k2 -> n2
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) col[16 * n2] = make_float2(br[n2], bi[n2]);
+    }
+    group_sync<TPF>(bar);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const float2 v = ex[k1 * ROW + t];
+      ar[k1] = v.x * rg.wr[k1] + v.y * rg.wi[k1];             // * conj(W^{t k1})
+      ai[k1] = v.y * rg.wr[k1] - v.x * rg.wi[k1];
+    }
+    fft_reg<16>(ai, ar);                                      // inverse over k1 -> n1
+  }
+  // (pr,pi)[i] <- Z[N - (t + 256 i)]
+  __device__ static __forceinline__ void mirror(const float (&br)[16], const float (&bi)[16],
+                                                float (&pr)[16], float (&pi)[16], float2* ex, int t,
+                                                int bar) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ex[i * ROW + t] = make_float2(br[i], bi[i]);
+    group_sync<TPF>(bar);
+    const int pt = (256 - t) & 255;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int pk = (t == 0) ? ((16 - i) & 15) : (15 - i);
+      const float2 v = ex[pk * ROW + pt];
+      pr[i] = v.x; pi[i] = v.y;
+    }
+  }
+};
 
 // overlap-add envelope at block `blk`, offset r (< HOP) given w^2 of both halves
 __device__ __forceinline__ float ola_env(int blk, int frames, float w2lo, float w2hi) {
@@ -129,29 +241,26 @@ __device__ __forceinline__ float ola_env(int blk, int frames, float w2lo, float 
 // ---------------------------------------------------------------------------
 template <class G>
 struct Smem {
-  float2* tw;    // TW_ELEMS
+  float2* tw;    // TW_SMEM
   float* win;    // N
   float* hs;     // F   (H/N, or bin scale)
   float2* ex;    // groups * EX_ELEMS
   __device__ Smem(unsigned char* base, int groups) {
     tw = reinterpret_cast<float2*>(base);
-    ex = tw + G::TW_ELEMS;
+    ex = tw + G::TW_SMEM;
     win = reinterpret_cast<float*>(ex + groups * G::EX_ELEMS);
     hs = win + G::N;
   }
   static size_t bytes(int groups, int extra_floats_per_group = 0) {
-    return sizeof(float2) * (G::TW_ELEMS + (size_t)groups * G::EX_ELEMS) +
+    return sizeof(float2) * (G::TW_SMEM + (size_t)groups * G::EX_ELEMS) +
            sizeof(float) * (G::N + G::F + 3 + (size_t)groups * extra_floats_per_group);
   }
 };
 
 template <class G>
 __device__ __forceinline__ void load_tables(Smem<G>& sm, const float* window, const float2* twiddle) {
-  for (int i = threadIdx.x; i < G::N; i += blockDim.x) {
-    sm.win[i] = window[i];
-    const int k1 = i / G::R2, n2 = i % G::R2;
-    sm.tw[k1 * G::EXF + n2] = twiddle[i];
-  }
+  for (int i = threadIdx.x; i < G::N; i += blockDim.x) sm.win[i] = window[i];
+  G::load_twiddles(sm.tw, twiddle);
 }
 
 // ---------------------------------------------------------------------------
@@ -171,7 +280,7 @@ struct FilterArgs {
 };
 
 template <class G, int GROUPS>
-__global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const FilterArgs a) {
+__global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1) k_apply_filter(const FilterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   __shared__ FilterSegs segs;
@@ -182,11 +291,9 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const Filter
   if (a.H != nullptr) {
     for (int k = threadIdx.x; k < G::F; k += blockDim.x) sm.hs[k] = a.H[k] * inv_n;
   } else {
-    if (threadIdx.x == 0) {
-      build_segments(segs, a.fc, a.A, a.K, a.freqs, G::F);
-      if (segs.bad && a.status != nullptr && blockIdx.x == 0) *a.status = 1;
-    }
-    __syncthreads();
+    __shared__ float fkf[BABE_MAX_BREAKPOINTS];
+    build_segments_coop(segs, fkf, a.fc, a.A, a.K, a.freqs, G::F);
+    if (threadIdx.x == 0 && segs.bad && a.status != nullptr && blockIdx.x == 0) *a.status = 1;
     for (int k = threadIdx.x; k < G::F; k += blockDim.x)
       sm.hs[k] = bin_gain(segs, k, a.freqs[k]) * inv_n;
   }
@@ -196,6 +303,8 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const Filter
   const int t = threadIdx.x % G::TPF;
   const int bar = 1 + grp;
   float2* ex = sm.ex + grp * G::EX_ELEMS;
+  typename G::Regs regs;
+  G::init_regs(regs, a.twiddle, t);
   const long long n_items = (long long)a.B * a.items_per_row;
 
   for (long long item = (long long)blockIdx.x * GROUPS + grp; item < n_items;
@@ -209,24 +318,24 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const Filter
     float* yr = a.y + (size_t)row * a.T;
     const float* subr = a.sub ? a.sub + (size_t)row * a.T : nullptr;
     const float rs = a.row_scale ? a.row_scale[row] : 1.0f;
-    float carry[G::R1 / 2];
+    float carry[G::NT / 2];
 #pragma unroll
-    for (int i = 0; i < G::R1 / 2; ++i) carry[i] = 0.f;
+    for (int i = 0; i < G::NT / 2; ++i) carry[i] = 0.f;
     double acc = 0.0;
 
     for (int fA = fs; fA <= fe; fA += 2) {
-      float ar[G::R1], ai[G::R1], br[G::R2], bi[G::R2];
-      if (t < G::R2) {
+      float ar[G::NT], ai[G::NT], br[G::NF], bi[G::NF];
+      if (t < G::TT) {
         // ---- load 3 half-frames: samples fA*HOP + R2*j + t, j < 3*R1/2
-        float xs[G::R1 + G::R1 / 2];
+        float xs[G::NT + G::NT / 2];
         const long long base = (long long)fA * G::HOP + t;
 #pragma unroll
-        for (int j = 0; j < G::R1 + G::R1 / 2; ++j) {
-          const long long p = base + (long long)G::R2 * j;
+        for (int j = 0; j < G::NT + G::NT / 2; ++j) {
+          const long long p = base + (long long)G::TS * j;
           float v = (p < a.T) ? __ldg(xr + p) : 0.f;
           if (a.adjoint) {
-            const int blk = fA + j / (G::R1 / 2);
-            const int r = (j % (G::R1 / 2)) * G::R2 + t;
+            const int blk = fA + j / (G::NT / 2);
+            const int r = (j % (G::NT / 2)) * G::TS + t;
             const float wl = sm.win[r], wh = sm.win[r + G::HOP];
             v = (p < a.T) ? __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh)) : 0.f;
           }
@@ -234,28 +343,28 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const Filter
         }
         const bool hasB = (fA + 1) < a.frames;
 #pragma unroll
-        for (int n1 = 0; n1 < G::R1; ++n1) {
-          const float w = sm.win[G::R2 * n1 + t];
+        for (int n1 = 0; n1 < G::NT; ++n1) {
+          const float w = sm.win[G::TS * n1 + t];
           ar[n1] = xs[n1] * w;
-          ai[n1] = hasB ? xs[n1 + G::R1 / 2] * w : 0.f;
+          ai[n1] = hasB ? xs[n1 + G::NT / 2] * w : 0.f;
         }
       }
-      fwd_pair<G>(ar, ai, br, bi, ex, sm.tw, t, bar);
-      if (t < G::R1) {
+      G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
+      if (t < G::FT) {
 #pragma unroll
-        for (int k2 = 0; k2 < G::R2; ++k2) {
-          const int k = t + G::R1 * k2;
+        for (int k2 = 0; k2 < G::NF; ++k2) {
+          const int k = t + G::KS * k2;
           const float h = sm.hs[k <= G::N / 2 ? k : G::N - k];
           br[k2] *= h; bi[k2] *= h;
         }
       }
       group_sync<G::TPF>(bar);            // every thread has finished reading ex
-      inv_pair<G>(br, bi, ar, ai, ex, sm.tw, t, bar);
-      if (t < G::R2) {
+      G::inv(br, bi, ar, ai, ex, sm.tw, regs, t, bar);
+      if (t < G::TT) {
         // ---- window, overlap-add, normalise, store
 #pragma unroll
-        for (int n1 = 0; n1 < G::R1; ++n1) {
-          const float w = sm.win[G::R2 * n1 + t];
+        for (int n1 = 0; n1 < G::NT; ++n1) {
+          const float w = sm.win[G::TS * n1 + t];
           ar[n1] *= w; ai[n1] *= w;
         }
 #pragma unroll
@@ -263,10 +372,10 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const Filter
           const int blk = fA + half;
           const bool mine = (blk >= j0) && (blk < j1);
 #pragma unroll
-          for (int n1 = 0; n1 < G::R1 / 2; ++n1) {
+          for (int n1 = 0; n1 < G::NT / 2; ++n1) {
             float v = half == 0 ? __fadd_rn(ar[n1], carry[n1])
-                                : __fadd_rn(ar[n1 + G::R1 / 2], ai[n1]);
-            const int r = G::R2 * n1 + t;
+                                : __fadd_rn(ar[n1 + G::NT / 2], ai[n1]);
+            const int r = G::TS * n1 + t;
             const long long p = (long long)blk * G::HOP + r;
             if (mine && p < a.T) {
               if (!a.adjoint) {
@@ -281,7 +390,7 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_apply_filter(const Filter
           }
         }
 #pragma unroll
-        for (int n1 = 0; n1 < G::R1 / 2; ++n1) carry[n1] = ai[n1 + G::R1 / 2];
+        for (int n1 = 0; n1 < G::NT / 2; ++n1) carry[n1] = ai[n1 + G::NT / 2];
       }
       group_sync<G::TPF>(bar);            // ex free for the next pair
     }
@@ -319,7 +428,7 @@ struct StatsArgs {
 };
 
 template <class G, int GROUPS>
-__global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft_stats(const StatsArgs a) {
+__global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1) k_stft_stats(const StatsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   float* accbase = sm.hs + G::F + 3;
@@ -328,6 +437,8 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft_stats(const StatsArg
   const int t = threadIdx.x % G::TPF;
   const int bar = 1 + grp;
   float2* ex = sm.ex + grp * G::EX_ELEMS;
+  typename G::Regs regs;
+  G::init_regs(regs, a.twiddle, t);
   float* acc = accbase + (size_t)grp * 3 * G::F;
   for (int i = t; i < 3 * G::F; i += G::TPF) acc[i] = 0.f;
   __syncthreads();
@@ -341,20 +452,20 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft_stats(const StatsArg
     const float* xr = a.x + (size_t)row * a.T;
     const float* yr = a.y + (size_t)row * a.T;
     for (int f = f0; f < f1; ++f) {
-      float ar[G::R1], ai[G::R1], br[G::R2], bi[G::R2], pr[G::R2], pi[G::R2];
-      if (t < G::R2) {
+      float ar[G::NT], ai[G::NT], br[G::NF], bi[G::NF], pr[G::NF], pi[G::NF];
+      if (t < G::TT) {
         const long long base = (long long)f * G::HOP + t;
 #pragma unroll
-        for (int n1 = 0; n1 < G::R1; ++n1) {
-          const long long p = base + (long long)G::R2 * n1;
-          const float w = sm.win[G::R2 * n1 + t];
+        for (int n1 = 0; n1 < G::NT; ++n1) {
+          const long long p = base + (long long)G::TS * n1;
+          const float w = sm.win[G::TS * n1 + t];
           float xv = 0.f, yv = 0.f;
           if (p < a.T) {
             xv = __ldg(xr + p);
             yv = __ldg(yr + p);
             if (a.mode == 1) {
-              const int blk = f + (n1 >= G::R1 / 2 ? 1 : 0);
-              const int r = (n1 % (G::R1 / 2)) * G::R2 + t;
+              const int blk = f + (n1 >= G::NT / 2 ? 1 : 0);
+              const int r = (n1 % (G::NT / 2)) * G::TS + t;
               const float wl = sm.win[r], wh = sm.win[r + G::HOP];
               yv = __fdiv_rn(yv, ola_env(blk, a.frames, wl * wl, wh * wh));
             }
@@ -362,14 +473,14 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft_stats(const StatsArg
           ar[n1] = xv * w; ai[n1] = yv * w;
         }
       }
-      fwd_pair<G>(ar, ai, br, bi, ex, sm.tw, t, bar);
+      G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
       group_sync<G::TPF>(bar);
-      mirror_exchange<G>(br, bi, pr, pi, ex, t, bar);
-      if (t < G::R1) {
+      G::mirror(br, bi, pr, pi, ex, t, bar);
+      if (t < G::FT) {
 #pragma unroll
-        for (int k2 = 0; k2 <= G::R2 / 2; ++k2) {
-          if (k2 == G::R2 / 2 && t != 0) continue;
-          const int k = t + G::R1 * k2;
+        for (int k2 = 0; k2 <= G::NF / 2; ++k2) {
+          if (k2 == G::NF / 2 && t != 0) continue;
+          const int k = t + G::KS * k2;
           const float xre = 0.5f * (br[k2] + pr[k2]), xim = 0.5f * (bi[k2] - pi[k2]);
           const float yre = 0.5f * (bi[k2] + pi[k2]), yim = -0.5f * (br[k2] - pr[k2]);
           if (a.mode == 0) {
@@ -417,7 +528,7 @@ struct StftArgs {
 };
 
 template <class G, int GROUPS>
-__global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft(const StftArgs a) {
+__global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1) k_stft(const StftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   load_tables(sm, a.window, a.twiddle);
@@ -427,6 +538,8 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft(const StftArgs a) {
   const int t = threadIdx.x % G::TPF;
   const int bar = 1 + grp;
   float2* ex = sm.ex + grp * G::EX_ELEMS;
+  typename G::Regs regs;
+  G::init_regs(regs, a.twiddle, t);
   const long long n_items = (long long)a.B * a.items_per_row;
   for (long long item = (long long)blockIdx.x * GROUPS + grp; item < n_items;
        item += (long long)gridDim.x * GROUPS) {
@@ -437,37 +550,37 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_stft(const StftArgs a) {
     for (int pp = p0; pp < p0 + a.ppi && 2 * pp < a.frames; ++pp) {
       const int fA = 2 * pp;
       const bool hasB = fA + 1 < a.frames;
-      float ar[G::R1], ai[G::R1], br[G::R2], bi[G::R2], pr[G::R2], pi[G::R2];
-      if (t < G::R2) {
-        float xs[G::R1 + G::R1 / 2];
+      float ar[G::NT], ai[G::NT], br[G::NF], bi[G::NF], pr[G::NF], pi[G::NF];
+      if (t < G::TT) {
+        float xs[G::NT + G::NT / 2];
         const long long base = (long long)fA * G::HOP + t;
 #pragma unroll
-        for (int j = 0; j < G::R1 + G::R1 / 2; ++j) {
-          const long long p = base + (long long)G::R2 * j;
+        for (int j = 0; j < G::NT + G::NT / 2; ++j) {
+          const long long p = base + (long long)G::TS * j;
           float v = (p < a.T) ? __ldg(xr + p) : 0.f;
           if (a.in_env_div && p < a.T) {
-            const int blk = fA + j / (G::R1 / 2);
-            const int r = (j % (G::R1 / 2)) * G::R2 + t;
+            const int blk = fA + j / (G::NT / 2);
+            const int r = (j % (G::NT / 2)) * G::TS + t;
             const float wl = sm.win[r], wh = sm.win[r + G::HOP];
             v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
           }
           xs[j] = v;
         }
 #pragma unroll
-        for (int n1 = 0; n1 < G::R1; ++n1) {
-          const float w = sm.win[G::R2 * n1 + t];
+        for (int n1 = 0; n1 < G::NT; ++n1) {
+          const float w = sm.win[G::TS * n1 + t];
           ar[n1] = xs[n1] * w;
-          ai[n1] = hasB ? xs[n1 + G::R1 / 2] * w : 0.f;
+          ai[n1] = hasB ? xs[n1 + G::NT / 2] * w : 0.f;
         }
       }
-      fwd_pair<G>(ar, ai, br, bi, ex, sm.tw, t, bar);
+      G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
       group_sync<G::TPF>(bar);
-      mirror_exchange<G>(br, bi, pr, pi, ex, t, bar);
-      if (t < G::R1) {
+      G::mirror(br, bi, pr, pi, ex, t, bar);
+      if (t < G::FT) {
 #pragma unroll
-        for (int k2 = 0; k2 <= G::R2 / 2; ++k2) {
-          if (k2 == G::R2 / 2 && t != 0) continue;
-          const int k = t + G::R1 * k2;
+        for (int k2 = 0; k2 <= G::NF / 2; ++k2) {
+          if (k2 == G::NF / 2 && t != 0) continue;
+          const int k = t + G::KS * k2;
           const float s = sm.hs[k];
           // frame A = (Z + conj(Zp))/2, frame B = (Z - conj(Zp))/(2i)
           float2 XA, XB;
@@ -494,7 +607,7 @@ struct IstftArgs {
 };
 
 template <class G, int GROUPS>
-__global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_istft(const IstftArgs a) {
+__global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1) k_istft(const IstftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   load_tables(sm, a.window, a.twiddle);
@@ -506,6 +619,8 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_istft(const IstftArgs a) 
   const int t = threadIdx.x % G::TPF;
   const int bar = 1 + grp;
   float2* ex = sm.ex + grp * G::EX_ELEMS;
+  typename G::Regs regs;
+  G::init_regs(regs, a.twiddle, t);
   const long long n_items = (long long)a.B * a.items_per_row;
   for (long long item = (long long)blockIdx.x * GROUPS + grp; item < n_items;
        item += (long long)gridDim.x * GROUPS) {
@@ -516,16 +631,16 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_istft(const IstftArgs a) 
     const int fe = min(j1 - 1, a.frames - 1);
     const float2* Xr = reinterpret_cast<const float2*>(a.X) + (size_t)row * G::F * a.frames;
     float* yr = a.y + (size_t)row * a.out_len;
-    float carry[G::R1 / 2];
+    float carry[G::NT / 2];
 #pragma unroll
-    for (int i = 0; i < G::R1 / 2; ++i) carry[i] = 0.f;
+    for (int i = 0; i < G::NT / 2; ++i) carry[i] = 0.f;
     for (int fA = fs; fA <= fe; fA += 2) {
-      float ar[G::R1], ai[G::R1], br[G::R2], bi[G::R2];
+      float ar[G::NT], ai[G::NT], br[G::NF], bi[G::NF];
       const bool hasB = fA + 1 < a.frames;
-      if (t < G::R1) {
+      if (t < G::FT) {
 #pragma unroll
-        for (int k2 = 0; k2 < G::R2; ++k2) {
-          const int k = t + G::R1 * k2;
+        for (int k2 = 0; k2 < G::NF; ++k2) {
+          const int k = t + G::KS * k2;
           const bool mir = k > G::N / 2;
           const int kk = mir ? G::N - k : k;
           const float2* src = Xr + (size_t)kk * a.frames + fA;
@@ -538,11 +653,11 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_istft(const IstftArgs a) 
           bi[k2] = (XA.y + XB.x) * h;
         }
       }
-      inv_pair<G>(br, bi, ar, ai, ex, sm.tw, t, bar);
-      if (t < G::R2) {
+      G::inv(br, bi, ar, ai, ex, sm.tw, regs, t, bar);
+      if (t < G::TT) {
 #pragma unroll
-        for (int n1 = 0; n1 < G::R1; ++n1) {
-          const float w = sm.win[G::R2 * n1 + t];
+        for (int n1 = 0; n1 < G::NT; ++n1) {
+          const float w = sm.win[G::TS * n1 + t];
           ar[n1] *= w; ai[n1] *= w;
         }
 #pragma unroll
@@ -550,10 +665,10 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_istft(const IstftArgs a) 
           const int blk = fA + half;
           const bool mine = (blk >= j0) && (blk < j1);
 #pragma unroll
-          for (int n1 = 0; n1 < G::R1 / 2; ++n1) {
+          for (int n1 = 0; n1 < G::NT / 2; ++n1) {
             float v = half == 0 ? __fadd_rn(ar[n1], carry[n1])
-                                : __fadd_rn(ar[n1 + G::R1 / 2], ai[n1]);
-            const int r = G::R2 * n1 + t;
+                                : __fadd_rn(ar[n1 + G::NT / 2], ai[n1]);
+            const int r = G::TS * n1 + t;
             const long long p = (long long)blk * G::HOP + r;
             if (mine && p < a.out_len) {
               if (a.out_env_div) {
@@ -565,7 +680,7 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_istft(const IstftArgs a) 
           }
         }
 #pragma unroll
-        for (int n1 = 0; n1 < G::R1 / 2; ++n1) carry[n1] = ai[n1 + G::R1 / 2];
+        for (int n1 = 0; n1 < G::NT / 2; ++n1) carry[n1] = ai[n1 + G::NT / 2];
       }
       group_sync<G::TPF>(bar);
     }
@@ -575,6 +690,9 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, 1) k_istft(const IstftArgs a) 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+template <class G, int GROUPS>
+static constexpr int ctas_per_sm() { return G::TPF * GROUPS <= 256 ? 2 : 1; }
+
 static int pick_chunk(long long rows, int units_per_row, long long capacity, int max_chunk,
                       bool odd_only) {
   // chunk size (units per work item) minimising (rounds * cost per item)
@@ -597,10 +715,10 @@ static int launch_apply_filter(FilterArgs a, void* ws, size_t ws_bytes, cudaStre
   a.frames = 1 + a.T / hop;
   a.nblk = (a.T - 1) / hop + 1;
   const int sms = sm_count();
-  a.bpi = pick_chunk(a.B, a.nblk, (long long)sms * GROUPS, 31, true);
+  a.bpi = pick_chunk(a.B, a.nblk, (long long)sms * GROUPS * ctas_per_sm<G, GROUPS>(), 31, true);
   a.items_per_row = (a.nblk + a.bpi - 1) / a.bpi;
   const long long items = (long long)a.B * a.items_per_row;
-  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
+  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms * ctas_per_sm<G, GROUPS>());
   const size_t smem = Smem<G>::bytes(GROUPS);
   a.item_sumsq = nullptr;
   if (a.row_sumsq != nullptr) {
@@ -621,10 +739,10 @@ template <class G, int GROUPS>
 static int launch_stats(StatsArgs a, double* abc, void* ws, size_t ws_bytes, cudaStream_t st) {
   a.frames = 1 + a.T / G::HOP;
   const int sms = sm_count();
-  a.fpi = pick_chunk(a.B, a.frames, (long long)sms * GROUPS, 32, false);
+  a.fpi = pick_chunk(a.B, a.frames, (long long)sms * GROUPS * ctas_per_sm<G, GROUPS>(), 32, false);
   a.items_per_row = (a.frames + a.fpi - 1) / a.fpi;
   const long long items = (long long)a.B * a.items_per_row;
-  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
+  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms * ctas_per_sm<G, GROUPS>());
   const size_t need = (size_t)grid * GROUPS * 3 * G::F * sizeof(float);
   BABE_REQUIRE(ws != nullptr && ws_bytes >= need, BABE_EBADARG,
                "stft_stats: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -645,10 +763,10 @@ static int launch_stft(StftArgs a, cudaStream_t st) {
   if (a.frames <= 0) a.frames = 1 + a.T / G::HOP;
   const int pairs = (a.frames + 1) / 2;
   const int sms = sm_count();
-  a.ppi = pick_chunk(a.B, pairs, (long long)sms * GROUPS, 16, false);
+  a.ppi = pick_chunk(a.B, pairs, (long long)sms * GROUPS * ctas_per_sm<G, GROUPS>(), 16, false);
   a.items_per_row = (pairs + a.ppi - 1) / a.ppi;
   const long long items = (long long)a.B * a.items_per_row;
-  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
+  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms * ctas_per_sm<G, GROUPS>());
   const size_t smem = Smem<G>::bytes(GROUPS);
   auto kern = k_stft<G, GROUPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -660,10 +778,10 @@ template <class G, int GROUPS>
 static int launch_istft(IstftArgs a, cudaStream_t st) {
   a.nblk = (a.out_len - 1) / G::HOP + 1;
   const int sms = sm_count();
-  a.bpi = pick_chunk(a.B, a.nblk, (long long)sms * GROUPS, 31, true);
+  a.bpi = pick_chunk(a.B, a.nblk, (long long)sms * GROUPS * ctas_per_sm<G, GROUPS>(), 31, true);
   a.items_per_row = (a.nblk + a.bpi - 1) / a.bpi;
   const long long items = (long long)a.B * a.items_per_row;
-  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms);
+  const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms * ctas_per_sm<G, GROUPS>());
   const size_t smem = Smem<G>::bytes(GROUPS);
   auto kern = k_istft<G, GROUPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -674,10 +792,10 @@ static int launch_istft(IstftArgs a, cudaStream_t st) {
 // groups per CTA chosen so that one CTA fills an SM's register file / smem
 #define BABE_DISPATCH_NFFT(nfft, CALL)                                   \
   switch (nfft) {                                                        \
-    case 4096: { using G = Geo<64, 64>; constexpr int GR = 4; CALL; }    \
-    case 2048: { using G = Geo<32, 64>; constexpr int GR = 4; CALL; }    \
-    case 1024: { using G = Geo<32, 32>; constexpr int GR = 8; CALL; }    \
-    case 512:  { using G = Geo<16, 32>; constexpr int GR = 8; CALL; }    \
+    case 4096: { using G = Core3; constexpr int GR = 1; CALL; }          \
+    case 2048: { using G = Core2<32, 64>; constexpr int GR = 4; CALL; }    \
+    case 1024: { using G = Core2<32, 32>; constexpr int GR = 8; CALL; }    \
+    case 512:  { using G = Core2<16, 32>; constexpr int GR = 8; CALL; }    \
     default: break;                                                      \
   }
 
@@ -692,21 +810,12 @@ extern "C" int babe_stft_supported(int nfft) {
 extern "C" int babe_stft_tables_host(int nfft, float* window_host, float* twiddle_host) {
   BABE_REQUIRE(babe_stft_supported(nfft), BABE_EUNSUPPORTED, "unsupported NFFT %d", nfft);
   BABE_REQUIRE(window_host && twiddle_host, BABE_EBADARG, "null table pointer");
-  int r1 = 0, r2 = 0;
-  switch (nfft) {
-    case 4096: r1 = 64; r2 = 64; break;
-    case 2048: r1 = 32; r2 = 64; break;
-    case 1024: r1 = 32; r2 = 32; break;
-    default: r1 = 16; r2 = 32; break;
-  }
-  for (int n = 0; n < nfft; ++n)
+  for (int n = 0; n < nfft; ++n) {
     window_host[n] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * (double)n / (double)nfft));
-  for (int k1 = 0; k1 < r1; ++k1)
-    for (int n2 = 0; n2 < r2; ++n2) {
-      const double ang = -2.0 * M_PI * (double)((long long)k1 * n2 % nfft) / (double)nfft;
-      twiddle_host[2 * (k1 * r2 + n2)] = (float)cos(ang);
-      twiddle_host[2 * (k1 * r2 + n2) + 1] = (float)sin(ang);
-    }
+    const double ang = -2.0 * M_PI * (double)n / (double)nfft;
+    twiddle_host[2 * n] = (float)cos(ang);
+    twiddle_host[2 * n + 1] = (float)sin(ang);
+  }
   return BABE_OK;
 }
 
@@ -742,7 +851,7 @@ extern "C" size_t babe_stft_stats_workspace(int B, int T, int nfft) {
   (void)B; (void)T;
   if (!babe_stft_supported(nfft)) return 0;
   const int sms = sm_count();
-  return (size_t)sms * 8 * 3 * (nfft / 2 + 1) * sizeof(float);
+  return (size_t)sms * 16 * 3 * (nfft / 2 + 1) * sizeof(float);
 }
 
 extern "C" int babe_stft_stats(const float* x, const float* y, int B, int T, int nfft,
@@ -758,10 +867,10 @@ extern "C" int babe_stft_stats(const float* x, const float* y, int B, int T, int
   a.twiddle = reinterpret_cast<const float2*>(twiddle); a.mode = mode;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (nfft) {
-    case 4096: return launch_stats<Geo<64, 64>, 3>(a, abc, workspace, workspace_bytes, st);
-    case 2048: return launch_stats<Geo<32, 64>, 4>(a, abc, workspace, workspace_bytes, st);
-    case 1024: return launch_stats<Geo<32, 32>, 8>(a, abc, workspace, workspace_bytes, st);
-    case 512: return launch_stats<Geo<16, 32>, 8>(a, abc, workspace, workspace_bytes, st);
+    case 4096: return launch_stats<Core3, 1>(a, abc, workspace, workspace_bytes, st);
+    case 2048: return launch_stats<Core2<32, 64>, 4>(a, abc, workspace, workspace_bytes, st);
+    case 1024: return launch_stats<Core2<32, 32>, 8>(a, abc, workspace, workspace_bytes, st);
+    case 512: return launch_stats<Core2<16, 32>, 8>(a, abc, workspace, workspace_bytes, st);
   }
   return BABE_EUNSUPPORTED;
 }

@@ -45,7 +45,7 @@ int babe_sm_count(void);
 int babe_stft_supported(int nfft);
 /* Fills HOST arrays: window_host[nfft] = periodic Hamming window
  * (utils/blind_bwe_utils.py:19), twiddle_host[2*nfft] = interleaved (re,im) of
- * exp(-2*pi*i*n2*k1/nfft) laid out [k1][n2] for the two-pass in-register FFT.
+ * the nfft-th roots of unity exp(-2*pi*i*m/nfft), m < nfft.
  * The caller uploads them once per NFFT and passes the device copies below. */
 int babe_stft_tables_host(int nfft, float* window_host, float* twiddle_host);
 

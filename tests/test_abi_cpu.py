@@ -46,10 +46,7 @@ def test_host_tables(handle):
         assert np.allclose(win, 0.54 - 0.46 * np.cos(2 * np.pi * n / nfft), atol=1e-7)
         c = tw[0::2] + 1j * tw[1::2]
         assert np.allclose(np.abs(c), 1.0, atol=1e-6)
-        r1 = {4096: 64, 2048: 32, 1024: 32, 512: 16}[nfft]
-        r2 = nfft // r1
-        k1, n2 = 3, 5
-        assert np.allclose(c[k1 * r2 + n2], np.exp(-2j * np.pi * k1 * n2 / nfft), atol=1e-6)
+        assert np.allclose(c, np.exp(-2j * np.pi * n / nfft), atol=1e-6)
 
 
 def test_no_cpu_fallback():
