@@ -57,6 +57,7 @@ struct Core2 {
   static constexpr int R1 = R1_, R2 = R2_;
   static constexpr int N = R1 * R2, HOP = N / 2, F = N / 2 + 1;
   static constexpr int TPF = R1 > R2 ? R1 : R2;
+  static constexpr int MIN_CTAS = 1;                         // register-heavy: one CTA per SM
   static constexpr int NT = R1, TS = R2, TT = R2;
   static constexpr int NF = R2, KS = R1, FT = R1;
   static constexpr int EXF = R2 + 1;                        // forward exchange  [k1][n2]
@@ -138,6 +139,7 @@ struct Core2 {
 struct Core3 {
   static constexpr int N = 4096, HOP = 2048, F = 2049;
   static constexpr int TPF = 256;
+  static constexpr int MIN_CTAS = 2;                         // <= 128 registers: two CTAs per SM
   static constexpr int NT = 16, TS = 256, TT = 256;
   static constexpr int NF = 16, KS = 256, FT = 256;
   static constexpr int ROW = 257;
@@ -264,6 +266,41 @@ __device__ __forceinline__ void load_tables(Smem<G>& sm, const float* window, co
 }
 
 // ---------------------------------------------------------------------------
+// asynchronous global -> shared staging of one frame pair's input (3 half-frames)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// samples [fA*HOP, fA*HOP + 3*HOP) of the row, zero-filled beyond T
+template <class G>
+__device__ __forceinline__ void stage_pair(float* stage, const float* xr, int T, int fA, int t, bool vec16) {
+  const long long base = (long long)fA * G::HOP;
+  if (vec16) {
+#pragma unroll 2
+    for (int c = t; c < 3 * G::HOP / 4; c += G::TPF) {
+      const long long p = base + 4 * c;
+      const bool in = p < T;                              // T % 4 == 0: chunk entirely in or out
+      cp_async16(stage + 4 * c, xr + (in ? p : 0), in ? 16 : 0);
+    }
+  } else {
+#pragma unroll 4
+    for (int c = t; c < 3 * G::HOP; c += G::TPF) {
+      const long long p = base + c;
+      const bool in = p < T;
+      cp_async4(stage + c, xr + (in ? p : 0), in ? 4 : 0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K1: fused STFT -> H -> iSTFT  (forward and adjoint)
 // ---------------------------------------------------------------------------
 struct FilterArgs {
@@ -280,7 +317,7 @@ struct FilterArgs {
 };
 
 template <class G, int GROUPS>
-__global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1) k_apply_filter(const FilterArgs a) {
+__global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_apply_filter(const FilterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   __shared__ FilterSegs segs;
@@ -303,9 +340,11 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1)
   const int t = threadIdx.x % G::TPF;
   const int bar = 1 + grp;
   float2* ex = sm.ex + grp * G::EX_ELEMS;
+  float* stage = sm.hs + ((G::F + 3) & ~3) + (size_t)grp * 3 * G::HOP;   // 16-byte aligned
   typename G::Regs regs;
   G::init_regs(regs, a.twiddle, t);
   const long long n_items = (long long)a.B * a.items_per_row;
+  const bool vec16 = (a.T % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
 
   for (long long item = (long long)blockIdx.x * GROUPS + grp; item < n_items;
        item += (long long)gridDim.x * GROUPS) {
@@ -323,17 +362,22 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1)
     for (int i = 0; i < G::NT / 2; ++i) carry[i] = 0.f;
     double acc = 0.0;
 
+    bool staged = false;
     for (int fA = fs; fA <= fe; fA += 2) {
       float ar[G::NT], ai[G::NT], br[G::NF], bi[G::NF];
+      // ---- the pair's 3 half-frames come through the cp.async staging buffer: the
+      // copy for pair p+1 is issued while pair p is being transformed
+      if (!staged) stage_pair<G>(stage, xr, a.T, fA, t, vec16);
+      cp_async_wait_all();
+      group_sync<G::TPF>(bar);
       if (t < G::TT) {
-        // ---- load 3 half-frames: samples fA*HOP + R2*j + t, j < 3*R1/2
         float xs[G::NT + G::NT / 2];
         const long long base = (long long)fA * G::HOP + t;
 #pragma unroll
         for (int j = 0; j < G::NT + G::NT / 2; ++j) {
-          const long long p = base + (long long)G::TS * j;
-          float v = (p < a.T) ? __ldg(xr + p) : 0.f;
+          float v = stage[G::TS * j + t];                    // zero beyond T
           if (a.adjoint) {
+            const long long p = base + (long long)G::TS * j;
             const int blk = fA + j / (G::NT / 2);
             const int r = (j % (G::NT / 2)) * G::TS + t;
             const float wl = sm.win[r], wh = sm.win[r + G::HOP];
@@ -349,6 +393,9 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1)
           ai[n1] = hasB ? xs[n1 + G::NT / 2] * w : 0.f;
         }
       }
+      G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);   // its barriers order the stage reads
+      staged = (fA + 2 <= fe);
+      if (staged) stage_pair<G>(stage, xr, a.T, fA + 2, t, vec16);
       G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
       if (t < G::FT) {
 #pragma unroll
@@ -428,7 +475,7 @@ struct StatsArgs {
 };
 
 template <class G, int GROUPS>
-__global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1) k_stft_stats(const StatsArgs a) {
+__global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_stft_stats(const StatsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   float* accbase = sm.hs + G::F + 3;
@@ -528,7 +575,7 @@ struct StftArgs {
 };
 
 template <class G, int GROUPS>
-__global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1) k_stft(const StftArgs a) {
+__global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_stft(const StftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   load_tables(sm, a.window, a.twiddle);
@@ -607,7 +654,7 @@ struct IstftArgs {
 };
 
 template <class G, int GROUPS>
-__global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1) k_istft(const IstftArgs a) {
+__global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_istft(const IstftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
   load_tables(sm, a.window, a.twiddle);
@@ -691,7 +738,7 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::TPF* GROUPS <= 256 ? 2 : 1)
 // host side
 // ---------------------------------------------------------------------------
 template <class G, int GROUPS>
-static constexpr int ctas_per_sm() { return G::TPF * GROUPS <= 256 ? 2 : 1; }
+static constexpr int ctas_per_sm() { return G::MIN_CTAS; }
 
 static int pick_chunk(long long rows, int units_per_row, long long capacity, int max_chunk,
                       bool odd_only) {
