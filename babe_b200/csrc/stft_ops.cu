@@ -766,7 +766,7 @@ static int launch_apply_filter(FilterArgs a, void* ws, size_t ws_bytes, cudaStre
   a.items_per_row = (a.nblk + a.bpi - 1) / a.bpi;
   const long long items = (long long)a.B * a.items_per_row;
   const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms * ctas_per_sm<G, GROUPS>());
-  const size_t smem = Smem<G>::bytes(GROUPS);
+  const size_t smem = Smem<G>::bytes(GROUPS, 3 * G::HOP) + 16;   // + cp.async staging per group
   a.item_sumsq = nullptr;
   if (a.row_sumsq != nullptr) {
     BABE_REQUIRE(ws != nullptr && ws_bytes >= (size_t)items * sizeof(double), BABE_EBADARG,
