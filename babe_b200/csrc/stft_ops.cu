@@ -396,7 +396,6 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_apply_filter(co
       G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);   // its barriers order the stage reads
       staged = (fA + 2 <= fe);
       if (staged) stage_pair<G>(stage, xr, a.T, fA + 2, t, vec16);
-      G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
       if (t < G::FT) {
 #pragma unroll
         for (int k2 = 0; k2 < G::NF; ++k2) {
