@@ -300,6 +300,27 @@ __device__ __forceinline__ void stage_pair(float* stage, const float* xr, int T,
   }
 }
 
+// samples [f*HOP, f*HOP + N) of the row (one frame), zero-filled beyond T
+template <class G>
+__device__ __forceinline__ void stage_frame(float* stage, const float* xr, int T, int f, int t, bool vec16) {
+  const long long base = (long long)f * G::HOP;
+  if (vec16) {
+#pragma unroll 2
+    for (int c = t; c < G::N / 4; c += G::TPF) {
+      const long long p = base + 4 * c;
+      const bool in = p < T;
+      cp_async16(stage + 4 * c, xr + (in ? p : 0), in ? 16 : 0);
+    }
+  } else {
+#pragma unroll 4
+    for (int c = t; c < G::N; c += G::TPF) {
+      const long long p = base + c;
+      const bool in = p < T;
+      cp_async4(stage + c, xr + (in ? p : 0), in ? 4 : 0);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K1: fused STFT -> H -> iSTFT  (forward and adjoint)
 // ---------------------------------------------------------------------------
@@ -477,7 +498,7 @@ template <class G, int GROUPS>
 __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_stft_stats(const StatsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<G> sm(smem_raw, GROUPS);
-  float* accbase = sm.hs + G::F + 3;
+  float* accbase = sm.hs;                 // no filter table in this kernel: reuse its slot
   load_tables(sm, a.window, a.twiddle);
   const int grp = threadIdx.x / G::TPF;
   const int t = threadIdx.x % G::TPF;
@@ -487,6 +508,9 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_stft_stats(cons
   G::init_regs(regs, a.twiddle, t);
   float* acc = accbase + (size_t)grp * 3 * G::F;
   for (int i = t; i < 3 * G::F; i += G::TPF) acc[i] = 0.f;
+  // staging buffers (2 N floats per group) follow the accumulators, 16-byte aligned
+  float* stage = accbase + (((size_t)GROUPS * 3 * G::F + 3) & ~(size_t)3) + (size_t)grp * 2 * G::N;
+  const bool vec16 = (a.T % 4 == 0) && (((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15) == 0);
   __syncthreads();
 
   const long long n_items = (long long)a.B * a.items_per_row;
@@ -497,28 +521,34 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_stft_stats(cons
     const int f1 = min(f0 + a.fpi, a.frames);
     const float* xr = a.x + (size_t)row * a.T;
     const float* yr = a.y + (size_t)row * a.T;
+    bool staged = false;
     for (int f = f0; f < f1; ++f) {
       float ar[G::NT], ai[G::NT], br[G::NF], bi[G::NF], pr[G::NF], pi[G::NF];
+      // both signals' frame goes through the cp.async staging buffer; the copy of
+      // frame f+1 overlaps the transform of frame f
+      if (!staged) { stage_frame<G>(stage, xr, a.T, f, t, vec16); stage_frame<G>(stage + G::N, yr, a.T, f, t, vec16); }
+      cp_async_wait_all();
+      group_sync<G::TPF>(bar);
       if (t < G::TT) {
         const long long base = (long long)f * G::HOP + t;
 #pragma unroll
         for (int n1 = 0; n1 < G::NT; ++n1) {
           const long long p = base + (long long)G::TS * n1;
           const float w = sm.win[G::TS * n1 + t];
-          float xv = 0.f, yv = 0.f;
-          if (p < a.T) {
-            xv = __ldg(xr + p);
-            yv = __ldg(yr + p);
-            if (a.mode == 1) {
-              const int blk = f + (n1 >= G::NT / 2 ? 1 : 0);
-              const int r = (n1 % (G::NT / 2)) * G::TS + t;
-              const float wl = sm.win[r], wh = sm.win[r + G::HOP];
-              yv = __fdiv_rn(yv, ola_env(blk, a.frames, wl * wl, wh * wh));
-            }
+          const float xv = stage[G::TS * n1 + t];             // zero beyond T
+          float yv = stage[G::N + G::TS * n1 + t];
+          if (a.mode == 1 && p < a.T) {
+            const int blk = f + (n1 >= G::NT / 2 ? 1 : 0);
+            const int r = (n1 % (G::NT / 2)) * G::TS + t;
+            const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+            yv = __fdiv_rn(yv, ola_env(blk, a.frames, wl * wl, wh * wh));
           }
           ar[n1] = xv * w; ai[n1] = yv * w;
         }
       }
+      G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
+      staged = (f + 1 < f1);
+      if (staged) { stage_frame<G>(stage, xr, a.T, f + 1, t, vec16); stage_frame<G>(stage + G::N, yr, a.T, f + 1, t, vec16); }
       G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
       group_sync<G::TPF>(bar);
       G::mirror(br, bi, pr, pi, ex, t, bar);
@@ -793,7 +823,7 @@ static int launch_stats(StatsArgs a, double* abc, void* ws, size_t ws_bytes, cud
   BABE_REQUIRE(ws != nullptr && ws_bytes >= need, BABE_EBADARG,
                "stft_stats: workspace too small (%zu < %zu)", ws_bytes, need);
   a.partial = static_cast<float*>(ws);
-  const size_t smem = Smem<G>::bytes(GROUPS, 3 * G::F);
+  const size_t smem = Smem<G>::bytes(GROUPS, 3 * G::F + 2 * G::N) - sizeof(float) * (G::F + 3) + 32;
   auto kern = k_stft_stats<G, GROUPS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<grid, G::TPF * GROUPS, smem, st>>>(a);
