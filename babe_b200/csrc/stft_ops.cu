@@ -549,7 +549,6 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_stft_stats(cons
       G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
       staged = (f + 1 < f1);
       if (staged) { stage_frame<G>(stage, xr, a.T, f + 1, t, vec16); stage_frame<G>(stage + G::N, yr, a.T, f + 1, t, vec16); }
-      G::fwd(ar, ai, br, bi, ex, sm.tw, regs, t, bar);
       group_sync<G::TPF>(bar);
       G::mirror(br, bi, pr, pi, ex, t, bar);
       if (t < G::FT) {
