@@ -137,7 +137,7 @@ def run_ours(a):
         print(f"warning: --gpus {a.gpus} but WORLD_SIZE={world}", file=sys.stderr)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = not a.no_autotune
     chains = a.chains
     args, net, smp, y = build_world(device, chains, seed=rank)
     K, W = a.steps, a.warmup
@@ -201,7 +201,10 @@ def run_ours(a):
     profiling.enable(True)
     dev_run, _, _ = timed_run("device")
     profiling.enable(False)
-    e2e_run, h2d, d2h = timed_run("e2e")
+    if a.skip_e2e:                       # profiling runs (ncu) only need the device-resident leg
+        e2e_run, h2d, d2h = dev_run, 0, 0
+    else:
+        e2e_run, h2d, d2h = timed_run("e2e")
 
     # final gather of outputs and filter estimates: the only collective on the path
     xg = bd.gather_rows(y[:, :16].contiguous())
@@ -386,6 +389,8 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--shapes", default="")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
+    ap.add_argument("--no-autotune", action="store_true", help="profiling aid: cudnn.benchmark off")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
