@@ -218,7 +218,7 @@ __device__ __forceinline__ int find_octave(const BandArgs& a, int item) {
   return o;
 }
 
-__global__ void __launch_bounds__(CQT_THREADS) k_cqt_analysis(const BandArgs a) {
+__global__ void __launch_bounds__(CQT_THREADS, 2) k_cqt_analysis(const BandArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
   const int tile = blockIdx.x - a.tile0[o];
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(CQT_THREADS) k_cqt_analysis(const BandArgs a) 
   }
 }
 
-__global__ void __launch_bounds__(CQT_THREADS) k_cqt_synth_bands(const BandArgs a) {
+__global__ void __launch_bounds__(CQT_THREADS, 2) k_cqt_synth_bands(const BandArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
   const int tile = blockIdx.x - a.tile0[o];
@@ -435,7 +435,7 @@ static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int
   items = 0;
   for (int o = 0; o < p->numocts; ++o) {
     const int M = p->M[o];
-    int tb = std::max(1, std::min(p->binsoct, 4096 / M));
+    int tb = std::max(1, std::min(p->binsoct, 2048 / M));   // <= 2048 points per CTA: more, smaller CTAs
     a.M[o] = M; a.tb[o] = tb; a.tile0[o] = items;
     a.fm[o] = to_dev(p->fm[o]);
     a.rootsm[o] = reinterpret_cast<const float2*>(p->rootsm[o]);

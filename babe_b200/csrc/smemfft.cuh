@@ -89,7 +89,8 @@ BABE_HD void stockham_stage(const float2* in, float2* out, int n, int stride, in
 // butterfly per task, which leaves most of the CTA idle for R = 13..23):
 //   out[u] = sum_t in[t] W_n^{t (k step + u n/R)}
 // -- the stage twiddle and the DFT weight are one root lookup per term.
-BABE_HD void stockham_stage_wide(int R, const float2* in, float2* out, int n, int stride, int nseq,
+template <int R>
+BABE_HD void stockham_stage_wide(const float2* in, float2* out, int n, int stride, int nseq,
                                  int Ns, const float2* wn, int tid, int nthreads) {
   const int m = n / R;
   const int tw_step = n / (Ns * R);
@@ -102,16 +103,25 @@ BABE_HD void stockham_stage_wide(int R, const float2* in, float2* out, int n, in
     int inc = k * tw_step + u * nr;
     if (inc >= n) inc -= n;
     const float2* src = in + seq * stride + j;
-    float2 acc = src[0];
+    // all 2(R-1) shared-memory loads are issued before the multiply-adds (ILP)
+    float2 v[R], w[R];
+    v[0] = src[0];
     int idx = 0;
+#pragma unroll
     for (int t = 1; t < R; ++t) {
       idx += inc;
       if (idx >= n) idx -= n;
-      const float2 v = src[t * m], w = wn[idx];
-      acc.x += v.x * w.x - v.y * w.y;
-      acc.y += v.x * w.y + v.y * w.x;
+      v[t] = src[t * m];
+      w[t] = wn[idx];
     }
-    out[seq * stride + (j - k) * R + k + u * Ns] = acc;
+    float2 acc = v[0], acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 1; t < R; ++t) {
+      float2& a = (t & 1) ? acc : acc2;               // two accumulation chains
+      a.x += v[t].x * w[t].x - v[t].y * w[t].y;
+      a.y += v[t].x * w[t].y + v[t].y * w[t].x;
+    }
+    out[seq * stride + (j - k) * R + k + u * Ns] = make_float2(acc.x + acc2.x, acc.y + acc2.y);
   }
 }
 
@@ -135,14 +145,14 @@ BABE_HD float2* smem_fft(float2* a, float2* b, const FftFactors& f, int stride, 
       case 3: stockham_stage<3>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       case 4: stockham_stage<4>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       case 5: stockham_stage<5>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 7: stockham_stage_wide(7, src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 7: stockham_stage_wide<7>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       case 8: stockham_stage<8>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 11: stockham_stage_wide(11, src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 13: stockham_stage_wide(13, src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 11: stockham_stage_wide<11>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 13: stockham_stage_wide<13>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       case 16: stockham_stage<16>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 17: stockham_stage_wide(17, src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 19: stockham_stage_wide(19, src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 23: stockham_stage_wide(23, src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 17: stockham_stage_wide<17>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 19: stockham_stage_wide<19>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 23: stockham_stage_wide<23>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       default: break;
     }
     Ns *= r;
