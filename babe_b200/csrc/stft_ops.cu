@@ -362,6 +362,13 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_apply_filter(co
   const int bar = 1 + grp;
   float2* ex = sm.ex + grp * G::EX_ELEMS;
   float* stage = sm.hs + ((G::F + 3) & ~3) + (size_t)grp * 3 * G::HOP;   // 16-byte aligned
+  // reciprocal overlap-add envelope of interior blocks (two frames overlap), shared by the groups
+  float* ienv = sm.hs + ((G::F + 3) & ~3) + (size_t)GROUPS * 3 * G::HOP;
+  for (int r = threadIdx.x; r < G::HOP; r += blockDim.x) {
+    const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+    ienv[r] = __frcp_rn(__fadd_rn(wh * wh, wl * wl));
+  }
+  __syncthreads();
   typename G::Regs regs;
   G::init_regs(regs, a.twiddle, t);
   const long long n_items = (long long)a.B * a.items_per_row;
@@ -398,11 +405,15 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_apply_filter(co
         for (int j = 0; j < G::NT + G::NT / 2; ++j) {
           float v = stage[G::TS * j + t];                    // zero beyond T
           if (a.adjoint) {
-            const long long p = base + (long long)G::TS * j;
             const int blk = fA + j / (G::NT / 2);
             const int r = (j % (G::NT / 2)) * G::TS + t;
-            const float wl = sm.win[r], wh = sm.win[r + G::HOP];
-            v = (p < a.T) ? __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh)) : 0.f;
+            if (blk >= 1 && blk < a.frames) {
+              v *= ienv[r];                                    // interior block: 1/(w_lo^2 + w_hi^2)
+            } else {
+              const long long p = base + (long long)G::TS * j;
+              const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+              v = (p < a.T) ? __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh)) : 0.f;
+            }
           }
           xs[j] = v;
         }
@@ -446,13 +457,17 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_apply_filter(co
             const long long p = (long long)blk * G::HOP + r;
             if (mine && p < a.T) {
               if (!a.adjoint) {
-                const float wl = sm.win[r], wh = sm.win[r + G::HOP];
-                v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
+                if (blk >= 1 && blk < a.frames) {
+                  v *= ienv[r];
+                } else {
+                  const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+                  v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
+                }
                 if (subr) v -= subr[p];
               }
               v *= rs;
               yr[p] = v;
-              acc += (double)v * (double)v;
+              if (a.item_sumsq != nullptr) acc += (double)v * (double)v;
             }
           }
         }
@@ -794,7 +809,7 @@ static int launch_apply_filter(FilterArgs a, void* ws, size_t ws_bytes, cudaStre
   a.items_per_row = (a.nblk + a.bpi - 1) / a.bpi;
   const long long items = (long long)a.B * a.items_per_row;
   const int grid = (int)std::min<long long>((items + GROUPS - 1) / GROUPS, (long long)sms * ctas_per_sm<G, GROUPS>());
-  const size_t smem = Smem<G>::bytes(GROUPS, 3 * G::HOP) + 16;   // + cp.async staging per group
+  const size_t smem = Smem<G>::bytes(GROUPS, 3 * G::HOP) + sizeof(float) * G::HOP + 16;   // + staging per group + 1/env
   a.item_sumsq = nullptr;
   if (a.row_sumsq != nullptr) {
     BABE_REQUIRE(ws != nullptr && ws_bytes >= (size_t)items * sizeof(double), BABE_EBADARG,

@@ -230,6 +230,7 @@ def run_ours(a):
                 "share_of_step": round(o["ms_total"] / dev_run["ms"], 4),
                 "ops": {k: {"ms_avg": round(v["ms_avg"], 4), "GBps": round(v["gbs"], 1), "calls": v["calls"],
                             "share": round(v["ms_total"] / dev_run["ms"], 4)} for k, v in ops.items()}}
+    op_roof = operator_probe(device, peak) if not a.skip_e2e else None
     cpu = None
     if not a.no_cpu_baseline:
         cpu = cpu_baseline_sample(steps=1)
@@ -249,9 +250,54 @@ def run_ours(a):
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_run["ms"] / K, 3)},
         "gpu_launches": dev_run["launches"],
         "clocks": dev_run["clk"].summary() if dev_run.get("clk") else None,
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "operator_roofline": op_roof, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
+
+
+def operator_probe(device, peak):
+    """"operator % of HBM roofline" (second half of BASELINE.json's metric): the streaming
+    operators alone at a batch that fills the GPU (config 4: B=512 x T=2^17, NFFT=4096),
+    CUDA events, L2 flushed between iterations."""
+    from babe_b200 import ops
+    from cqt_nsgt_pytorch import CQT_nsgt
+    B, T = 512, 1 << 17
+    x = torch.randn(B, T, device=device) * 0.063
+    y = torch.randn(B, T, device=device) * 0.063
+    out = torch.empty_like(x)
+    f = torch.fft.rfftfreq(NFFT, d=1 / SR).to(device)
+    fc = torch.tensor([300.0, 600.0, 1000.0, 3000.0, 6000.0], device=device)
+    A = torch.tensor([-10.0, -15.0, -20.0, -30.0, -40.0], device=device)
+    cq = CQT_nsgt(7, 64, mode="oct", window=("kaiser", 1), fs=SR, audio_len=AUDIO_LEN, device=device)
+    xc = torch.randn(64, AUDIO_LEN, device=device) * 0.063
+    coefs = [None]
+    cases = {
+        "apply_filter": (lambda: ops.apply_filter(x, NFFT, freqs=f, fc=fc, A=A, out=out), 8 * B * T),
+        "apply_filter_adj": (lambda: ops.apply_filter(x, NFFT, freqs=f, fc=fc, A=A, adjoint=True, out=out), 8 * B * T),
+        "stft_stats": (lambda: ops.stft_stats(x, y, NFFT), 8 * B * T),
+        "cqt_analysis_B64": (lambda: coefs.__setitem__(0, cq.fwd(xc.unsqueeze(1))),
+                             64 * (4 * AUDIO_LEN + 8 * cq.plan.coef_per_row)),
+        "cqt_synthesis_B64": (lambda: cq.bwd(coefs[0]), 64 * (4 * AUDIO_LEN + 8 * cq.plan.coef_per_row)),
+        "hpf_DC_B64": (lambda: cq.apply_hpf_DC(xc), 64 * 8 * AUDIO_LEN),
+    }
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    res = {"shape": f"B={B} x T={T} (STFT ops), B=64 x T={AUDIO_LEN} (CQT ops)", "l2": "flushed between iterations"}
+    for name, (fn, nbytes) in cases.items():
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(7):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ms = sorted(ts)[len(ts) // 2]
+        gbs = nbytes / 1e9 / (ms / 1e3)
+        res[name] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    return res
 
 
 # ---------------------------------------------------------------------------
@@ -401,3 +447,6 @@ def main():
 
 if __name__ == "__main__":
     main()
+    import torch.distributed as _dist
+    if _dist.is_available() and _dist.is_initialized():
+        _dist.destroy_process_group()
