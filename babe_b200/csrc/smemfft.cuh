@@ -3,8 +3,8 @@
 // nseq independent complex sequences of length n (row stride `stride`, odd in
 // float2 units to stay bank-conflict free) are transformed by all threads of
 // the CTA.  Radices 16/8/4/2 use the in-register butterflies of regfft.cuh;
-// odd primes up to 23 use a direct r x r DFT with the r-th roots taken from
-// the n-th root table (n is a multiple of r), so any length whose prime
+// odd primes up to 23 use a conjugate-symmetric small DFT with compile-time
+// roots (dft_odd_sym), so any length whose prime
 // factors are <= 23 is supported -- enough for the non-power-of-two segment
 // lengths of the reference (184184 = 2^3*7*11*13*23, 132300 = 2^2*3^3*5^2*7^2,
 // 368368, 485100; conf/exp/*.yaml).
@@ -52,8 +52,42 @@ BABE_HD void dft_direct(float (&vr)[R], float (&vi)[R], const float2* wn, int n)
   for (int u = 0; u < R; ++u) { vr[u] = orr[u]; vi[u] = oi[u]; }
 }
 
+// Odd-prime DFT exploiting W^{(R-t)u} = conj(W^{tu}): with a_t = v_t + v_{R-t},
+// b_t = v_t - v_{R-t},  X_u = v_0 + sum_t a_t cos(2 pi t u/R) - i sum_t b_t sin(2 pi t u/R)
+// and X_{R-u} is the same with +i.  (R-1)^2 + O(R) real multiply-adds instead of
+// 4 R^2, and the roots are compile-time immediates (no table, no registers).
+template <int R>
+BABE_HD void dft_odd_sym(float (&vr)[R], float (&vi)[R]) {
+  constexpr int H = (R - 1) / 2;
+  float ar[H], ai[H], br[H], bi[H];
+#pragma unroll
+  for (int t = 1; t <= H; ++t) {
+    ar[t - 1] = vr[t] + vr[R - t]; ai[t - 1] = vi[t] + vi[R - t];
+    br[t - 1] = vr[t] - vr[R - t]; bi[t - 1] = vi[t] - vi[R - t];
+  }
+  const float x0r = vr[0], x0i = vi[0];
+  float s0r = x0r, s0i = x0i;
+#pragma unroll
+  for (int t = 0; t < H; ++t) { s0r += ar[t]; s0i += ai[t]; }
+  vr[0] = s0r; vi[0] = s0i;
+#pragma unroll
+  for (int u = 1; u <= H; ++u) {
+    float Ar = x0r, Ai = x0i, Br = 0.f, Bi = 0.f;
+#pragma unroll
+    for (int t = 1; t <= H; ++t) {
+      const int m = (t * u) % R;
+      const float c = odd_cos<R>(m), sn = odd_sin<R>(m);
+      Ar += ar[t - 1] * c; Ai += ai[t - 1] * c;
+      Br += br[t - 1] * sn; Bi += bi[t - 1] * sn;
+    }
+    // X_u = A - i B,  X_{R-u} = A + i B
+    vr[u] = Ar + Bi; vi[u] = Ai - Br;
+    vr[R - u] = Ar - Bi; vi[R - u] = Ai + Br;
+  }
+}
+
 template <int R> BABE_HD void butterfly(float (&vr)[R], float (&vi)[R], const float2* wn, int n) {
-  dft_direct<R>(vr, vi, wn, n);
+  dft_odd_sym<R>(vr, vi);
 }
 template <> BABE_HD void butterfly<2>(float (&vr)[2], float (&vi)[2], const float2*, int) { fft2(vr, vi); }
 template <> BABE_HD void butterfly<4>(float (&vr)[4], float (&vi)[4], const float2*, int) { fft4(vr, vi); }
@@ -145,14 +179,14 @@ BABE_HD float2* smem_fft(float2* a, float2* b, const FftFactors& f, int stride, 
       case 3: stockham_stage<3>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       case 4: stockham_stage<4>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       case 5: stockham_stage<5>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 7: stockham_stage_wide<7>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 7: stockham_stage<7>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       case 8: stockham_stage<8>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 11: stockham_stage_wide<11>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 13: stockham_stage_wide<13>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 11: stockham_stage<11>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 13: stockham_stage<13>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       case 16: stockham_stage<16>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 17: stockham_stage_wide<17>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 19: stockham_stage_wide<19>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 23: stockham_stage_wide<23>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 17: stockham_stage<17>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 19: stockham_stage<19>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 23: stockham_stage<23>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
       default: break;
     }
     Ns *= r;
