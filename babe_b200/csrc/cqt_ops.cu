@@ -23,6 +23,8 @@
 namespace babe {
 
 constexpr int CQT_THREADS = 256;
+constexpr int MAX_TB = 64;          // bands per CTA (tb <= 2048 / 32)
+constexpr int BAND_THREADS = 128;   // band kernels: 2048-point tiles -> 128 radix-16 tasks per stage
 constexpr int TILE_SEQ = 8;          // sequences per CTA in the two big-FFT passes
 constexpr int TW_LO = 1024;          // low part of the two-level twiddle tables
 
@@ -31,7 +33,7 @@ __device__ __forceinline__ float2 tw2(const float2* tab, int m) {
   return cmul(tab[m & (TW_LO - 1)], tab[TW_LO + (m >> 10)]);
 }
 
-static inline int odd_stride(int n) { return n | 1; }
+static inline int odd_stride(int n) { return padded_len(n); }
 
 // ---------------------------------------------------------------------------
 // pass 1: for a tile of n2, FFT over n1 (stride n2), twiddle W_Nc^{n2 k1},
@@ -46,9 +48,9 @@ struct PassArgs {
   int conj_out;          // pass 2: conjugate on store (inverse transforms)
 };
 
-__global__ void __launch_bounds__(CQT_THREADS) k_fft_cols(const PassArgs a) {
+__global__ void __launch_bounds__(CQT_THREADS, 3) k_fft_cols(const PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int S = a.N1 | 1;
+  const int S = padded_len(a.N1);
   float2* A = reinterpret_cast<float2*>(smem_raw);
   float2* Bf = A + TILE_SEQ * S;
   float2* roots = Bf + TILE_SEQ * S;
@@ -65,21 +67,21 @@ __global__ void __launch_bounds__(CQT_THREADS) k_fft_cols(const PassArgs a) {
     const int n2 = n2_0 + n2l;
     float2 v = make_float2(0.f, 0.f);
     if (n2 < a.N2) v = in[(size_t)a.N2 * n1 + n2];
-    A[n2l * S + n1] = v;
+    A[n2l * S + pad16(n1)] = v;
   }
   __syncthreads();
   const float2* res = smem_fft(A, Bf, a.f, S, TILE_SEQ, roots, tid, CQT_THREADS);
   for (int idx = tid; idx < TILE_SEQ * a.N1; idx += CQT_THREADS) {
     const int n2l = idx % TILE_SEQ, k1 = idx / TILE_SEQ;
     const int n2 = n2_0 + n2l;
-    if (n2 < a.N2) out[(size_t)k1 * a.N2 + n2] = cmul(res[n2l * S + k1], tw2(tw, n2 * k1));
+    if (n2 < a.N2) out[(size_t)k1 * a.N2 + n2] = cmul(res[n2l * S + pad16(k1)], tw2(tw, n2 * k1));
   }
 }
 
 // pass 2: for a tile of k1, FFT over n2 (contiguous), store Z[k1 + N1 k2]
-__global__ void __launch_bounds__(CQT_THREADS) k_fft_rows(const PassArgs a) {
+__global__ void __launch_bounds__(CQT_THREADS, 3) k_fft_rows(const PassArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int S = a.N2 | 1;
+  const int S = padded_len(a.N2);
   float2* A = reinterpret_cast<float2*>(smem_raw);
   float2* Bf = A + TILE_SEQ * S;
   float2* roots = Bf + TILE_SEQ * S;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(CQT_THREADS) k_fft_rows(const PassArgs a) {
     const int k1 = k1_0 + k1l;
     float2 v = make_float2(0.f, 0.f);
     if (k1 < a.N1) v = in[(size_t)k1 * a.N2 + n2];
-    A[k1l * S + n2] = v;
+    A[k1l * S + pad16(n2)] = v;
   }
   __syncthreads();
   const float2* res = smem_fft(A, Bf, a.f, S, TILE_SEQ, roots, tid, CQT_THREADS);
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(CQT_THREADS) k_fft_rows(const PassArgs a) {
     const int k1l = idx % TILE_SEQ, k2 = idx / TILE_SEQ;
     const int k1 = k1_0 + k1l;
     if (k1 < a.N1) {
-      float2 v = res[k1l * S + k2];
+      float2 v = res[k1l * S + pad16(k2)];
       if (a.conj_out) v.y = -v.y;
       out[(size_t)k1 + (size_t)a.N1 * k2] = v;
     }
@@ -218,79 +220,92 @@ __device__ __forceinline__ int find_octave(const BandArgs& a, int item) {
   return o;
 }
 
-__global__ void __launch_bounds__(CQT_THREADS, 2) k_cqt_analysis(const BandArgs a) {
+__global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_analysis(const BandArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
   const int tile = blockIdx.x - a.tile0[o];
-  const int M = a.M[o], S = M | 1, TB = a.tb[o];
+  const int M = a.M[o], S = padded_len(M), TB = a.tb[o];
   const int b0 = tile * TB;
   const int nb = min(TB, a.binsoct - b0);
   float2* A = reinterpret_cast<float2*>(smem_raw);
   float2* Bf = A + TB * S;
   float2* roots = Bf + TB * S;
   const int tid = threadIdx.x, row = blockIdx.y;
-  for (int i = tid; i < M; i += CQT_THREADS) roots[i] = a.rootsm[o][i];
+  for (int i = tid; i < M; i += BAND_THREADS) roots[i] = a.rootsm[o][i];
+  // band descriptors once per CTA (they would otherwise be chains of dependent global loads)
+  __shared__ int s_p[MAX_TB], s_lg[MAX_TB], s_off[MAX_TB];
+  for (int i = tid; i < nb; i += BAND_THREADS) {
+    const int j = o * a.binsoct + b0 + i;
+    s_p[i] = a.band_p[j]; s_lg[i] = a.band_lg[j]; s_off[i] = a.band_off[j];
+  }
+  __syncthreads();
   const float2* X = a.X + (size_t)row * (a.Nc + 1);
-  for (int idx = tid; idx < nb * M; idx += CQT_THREADS) {
+#pragma unroll 4
+  for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
     const int bl = idx / M, m = idx - bl * M;
-    const int j = o * a.binsoct + b0 + bl;
-    const int lg = a.band_lg[j], half = lg / 2;
+    const int lg = s_lg[bl], half = lg / 2;
     // buffer slot m holds window sample i with (i - half) mod M == m
     int i = m + half;
     if (i >= M) i -= M;
     float2 v = make_float2(0.f, 0.f);
     if (i < lg) {
-      const int k = a.band_p[j] - half + i;
+      const int k = s_p[bl] - half + i;
       if (k >= 0 && k <= a.Nc) {
-        float w = a.win[a.band_off[j] + i];
+        float w = a.win[s_off[bl] + i];
         if (a.scale) w *= a.scale[k];
         const float2 xv = X[k];
         v = make_float2(xv.x * w, -xv.y * w);      // conjugate: inverse FFT via forward
       }
     }
-    A[bl * S + m] = v;
+    A[bl * S + pad16(m)] = v;
   }
   __syncthreads();
-  const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, CQT_THREADS);
+  const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, BAND_THREADS);
   const float inv_m = 1.0f / (float)M;
   float2* out = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
-  for (int idx = tid; idx < nb * M; idx += CQT_THREADS) {
+  for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
     const int bl = idx / M, m = idx - bl * M;
-    const float2 v = res[bl * S + m];
+    const float2 v = res[bl * S + pad16(m)];
     out[(size_t)bl * M + m] = make_float2(v.x * inv_m, -v.y * inv_m);
   }
 }
 
-__global__ void __launch_bounds__(CQT_THREADS, 2) k_cqt_synth_bands(const BandArgs a) {
+__global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_synth_bands(const BandArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
   const int tile = blockIdx.x - a.tile0[o];
-  const int M = a.M[o], S = M | 1, TB = a.tb[o];
+  const int M = a.M[o], S = padded_len(M), TB = a.tb[o];
   const int b0 = tile * TB;
   const int nb = min(TB, a.binsoct - b0);
   float2* A = reinterpret_cast<float2*>(smem_raw);
   float2* Bf = A + TB * S;
   float2* roots = Bf + TB * S;
   const int tid = threadIdx.x, row = blockIdx.y;
-  for (int i = tid; i < M; i += CQT_THREADS) roots[i] = a.rootsm[o][i];
+  for (int i = tid; i < M; i += BAND_THREADS) roots[i] = a.rootsm[o][i];
   const float2* in = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
-  for (int idx = tid; idx < nb * M; idx += CQT_THREADS) {
+  __shared__ int s_lg[MAX_TB], s_off[MAX_TB];
+  for (int i = tid; i < nb; i += BAND_THREADS) {
+    const int j = o * a.binsoct + b0 + i;
+    s_lg[i] = a.band_lg[j]; s_off[i] = a.band_off[j];
+  }
+#pragma unroll 4
+  for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
     const int bl = idx / M, m = idx - bl * M;
-    A[bl * S + m] = in[(size_t)bl * M + m];
+    A[bl * S + pad16(m)] = in[(size_t)bl * M + m];
   }
   __syncthreads();
-  const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, CQT_THREADS);
+  const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, BAND_THREADS);
   float2* BS = a.BS + (size_t)row * a.sum_lg;
-  for (int idx = tid; idx < nb * M; idx += CQT_THREADS) {
+#pragma unroll 4
+  for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
     const int bl = idx / M, m = idx - bl * M;
-    const int j = o * a.binsoct + b0 + bl;
-    const int lg = a.band_lg[j], half = lg / 2;
+    const int lg = s_lg[bl], half = lg / 2;
     int i = m + half;
     if (i >= M) i -= M;
     if (i < lg) {
-      const float w = a.win[a.band_off[j] + i];
-      const float2 v = res[bl * S + m];
-      BS[a.band_off[j] + i] = make_float2(v.x * w, v.y * w);
+      const float w = a.win[s_off[bl] + i];
+      const float2 v = res[bl * S + pad16(m)];
+      BS[s_off[bl] + i] = make_float2(v.x * w, v.y * w);
     }
   }
 }
@@ -435,7 +450,7 @@ static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int
   items = 0;
   for (int o = 0; o < p->numocts; ++o) {
     const int M = p->M[o];
-    int tb = std::max(1, std::min(p->binsoct, 2048 / M));   // <= 2048 points per CTA: more, smaller CTAs
+    int tb = std::max(1, std::min(std::min(p->binsoct, MAX_TB), 2048 / M));   // <= 2048 points per CTA: more, smaller CTAs
     a.M[o] = M; a.tb[o] = tb; a.tile0[o] = items;
     a.fm[o] = to_dev(p->fm[o]);
     a.rootsm[o] = reinterpret_cast<const float2*>(p->rootsm[o]);
@@ -543,7 +558,7 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
   }
   a.win = win; a.scale = bin_scale; a.X = w.bufX;
   cudaFuncSetAttribute(k_cqt_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_cqt_analysis<<<dim3(items, B), CQT_THREADS, smem, st>>>(a);
+  k_cqt_analysis<<<dim3(items, B), BAND_THREADS, smem, st>>>(a);
   return check_launch("k_cqt_analysis");
 }
 
@@ -567,7 +582,7 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
   }
   a.win = win; a.scale = nullptr; a.BS = w.bufS;
   cudaFuncSetAttribute(k_cqt_synth_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_cqt_synth_bands<<<dim3(items, B), CQT_THREADS, smem, st>>>(a);
+  k_cqt_synth_bands<<<dim3(items, B), BAND_THREADS, smem, st>>>(a);
   rc = check_launch("k_cqt_synth_bands");
   if (rc) return rc;
   GatherArgs g{};

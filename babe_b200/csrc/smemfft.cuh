@@ -29,6 +29,13 @@ BABE_HD float2 cmul(float2 a, float2 b) {
 }
 BABE_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
+// Sequence element a lives at physical slot a + a/16: the first Stockham stage of
+// radix R writes with stride R (16 float2 = 128 B = all 32 banks), which without
+// the skew is a 16..32-way bank conflict (66 % of all wavefronts in the round-1
+// profile of k_cqt_analysis).
+BABE_HD int pad16(int a) { return a + (a >> 4); }
+BABE_HD int padded_len(int n) { return (n + (n >> 4) + 1) | 1; }
+
 template <int R>
 BABE_HD void dft_direct(float (&vr)[R], float (&vi)[R], const float2* wn, int n) {
   // r-th roots W_r^m = W_n^{m n/r}
@@ -104,18 +111,19 @@ BABE_HD void stockham_stage(const float2* in, float2* out, int n, int stride, in
   for (int q = tid; q < tasks; q += nthreads) {
     const int seq = q / m, j = q - seq * m;
     const int k = j % Ns;
-    const float2* src = in + seq * stride + j;
+    const float2* src = in + seq * stride;
     float vr[R], vi[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) {
-      float2 v = src[t * m];
+      float2 v = src[pad16(j + t * m)];
       if (t > 0 && k > 0) v = cmul(v, wn[t * k * tw_step]);
       vr[t] = v.x; vi[t] = v.y;
     }
     butterfly<R>(vr, vi, wn, n);
-    float2* dst = out + seq * stride + (j - k) * R + k;
+    float2* dst = out + seq * stride;
+    const int o0 = (j - k) * R + k;
 #pragma unroll
-    for (int t = 0; t < R; ++t) dst[t * Ns] = make_float2(vr[t], vi[t]);
+    for (int t = 0; t < R; ++t) dst[pad16(o0 + t * Ns)] = make_float2(vr[t], vi[t]);
   }
 }
 
@@ -136,16 +144,16 @@ BABE_HD void stockham_stage_wide(const float2* in, float2* out, int n, int strid
     const int k = j % Ns;
     int inc = k * tw_step + u * nr;
     if (inc >= n) inc -= n;
-    const float2* src = in + seq * stride + j;
+    const float2* src = in + seq * stride;
     // all 2(R-1) shared-memory loads are issued before the multiply-adds (ILP)
     float2 v[R], w[R];
-    v[0] = src[0];
+    v[0] = src[pad16(j)];
     int idx = 0;
 #pragma unroll
     for (int t = 1; t < R; ++t) {
       idx += inc;
       if (idx >= n) idx -= n;
-      v[t] = src[t * m];
+      v[t] = src[pad16(j + t * m)];
       w[t] = wn[idx];
     }
     float2 acc = v[0], acc2 = make_float2(0.f, 0.f);
@@ -155,7 +163,7 @@ BABE_HD void stockham_stage_wide(const float2* in, float2* out, int n, int strid
       a.x += v[t].x * w[t].x - v[t].y * w[t].y;
       a.y += v[t].x * w[t].y + v[t].y * w[t].x;
     }
-    out[seq * stride + (j - k) * R + k + u * Ns] = make_float2(acc.x + acc2.x, acc.y + acc2.y);
+    out[seq * stride + pad16((j - k) * R + k + u * Ns)] = make_float2(acc.x + acc2.x, acc.y + acc2.y);
   }
 }
 
