@@ -409,10 +409,9 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_apply_filter(co
             const int r = (j % (G::NT / 2)) * G::TS + t;
             if (blk >= 1 && blk < a.frames) {
               v *= ienv[r];                                    // interior block: 1/(w_lo^2 + w_hi^2)
-            } else {
-              const long long p = base + (long long)G::TS * j;
+            } else if (v != 0.f) {                             // edge blocks only; zero stays zero
               const float wl = sm.win[r], wh = sm.win[r + G::HOP];
-              v = (p < a.T) ? __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh)) : 0.f;
+              v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
             }
           }
           xs[j] = v;
@@ -449,25 +448,41 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_apply_filter(co
         for (int half = 0; half < 2; ++half) {
           const int blk = fA + half;
           const bool mine = (blk >= j0) && (blk < j1);
+          if (!mine) continue;
+          const long long p0 = (long long)blk * G::HOP;
+          float* yb = yr + p0;
+          // fast path (group-uniform): interior block entirely inside the row -> no per-sample tests
+          const bool fast = (blk >= 1) && (blk < a.frames) && (p0 + G::HOP <= a.T);
+          if (fast) {
 #pragma unroll
-          for (int n1 = 0; n1 < G::NT / 2; ++n1) {
-            float v = half == 0 ? __fadd_rn(ar[n1], carry[n1])
-                                : __fadd_rn(ar[n1 + G::NT / 2], ai[n1]);
-            const int r = G::TS * n1 + t;
-            const long long p = (long long)blk * G::HOP + r;
-            if (mine && p < a.T) {
+            for (int n1 = 0; n1 < G::NT / 2; ++n1) {
+              float v = half == 0 ? __fadd_rn(ar[n1], carry[n1])
+                                  : __fadd_rn(ar[n1 + G::NT / 2], ai[n1]);
+              const int r = G::TS * n1 + t;
               if (!a.adjoint) {
-                if (blk >= 1 && blk < a.frames) {
-                  v *= ienv[r];
-                } else {
-                  const float wl = sm.win[r], wh = sm.win[r + G::HOP];
-                  v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
-                }
-                if (subr) v -= subr[p];
+                v *= ienv[r];
+                if (subr) v -= subr[p0 + r];
               }
               v *= rs;
-              yr[p] = v;
+              yb[r] = v;
               if (a.item_sumsq != nullptr) acc += (double)v * (double)v;
+            }
+          } else {
+#pragma unroll
+            for (int n1 = 0; n1 < G::NT / 2; ++n1) {
+              float v = half == 0 ? __fadd_rn(ar[n1], carry[n1])
+                                  : __fadd_rn(ar[n1 + G::NT / 2], ai[n1]);
+              const int r = G::TS * n1 + t;
+              if (p0 + r < a.T) {
+                if (!a.adjoint) {
+                  const float wl = sm.win[r], wh = sm.win[r + G::HOP];
+                  v = __fdiv_rn(v, ola_env(blk, a.frames, wl * wl, wh * wh));
+                  if (subr) v -= subr[p0 + r];
+                }
+                v *= rs;
+                yb[r] = v;
+                if (a.item_sumsq != nullptr) acc += (double)v * (double)v;
+              }
             }
           }
         }
