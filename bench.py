@@ -222,10 +222,18 @@ def run_ours(a):
     stream = {k: v for k, v in ops.items() if v["bytes_avg"] > 1e6}
     dom = max(stream, key=lambda k: stream[k]["ms_total"]) if stream else None
     roof = None
+    traffic = None
+    try:                      # per-call DRAM traffic of the dominant operator from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if dom in tj and tj[dom].get("B") == chains:
+            traffic = tj[dom]["bytes"]
+    except Exception:
+        pass
     if dom:
         o = ops[dom]
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(o["gbs"], 1), "peak": peak, "unit": "GB/s",
-                "frac": round(o["gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(o["gbs"] / peak, 4), "traffic": traffic,
+                "algorithmic_bytes": int(o["bytes_avg"]), "peak_source": peak_src,
                 "avg_ms": round(o["ms_avg"], 4), "calls": o["calls"],
                 "share_of_step": round(o["ms_total"] / dev_run["ms"], 4),
                 "ops": {k: {"ms_avg": round(v["ms_avg"], 4), "GBps": round(v["gbs"], 1), "calls": v["calls"],
