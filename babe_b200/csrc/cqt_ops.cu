@@ -42,6 +42,7 @@ static inline int odd_stride(int n) { return padded_len(n); }
 struct PassArgs {
   const float2* in; float2* out;
   int Nc, N1, N2;
+  FastDiv div_n2;
   FftFactors f;
   const float2* roots;   // n-th roots of this pass
   const float2* tw_nc;   // two-level W_Nc (pass 1 only)
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(CQT_THREADS, 3) k_fft_rows(const PassArgs a) {
   const float2* in = a.in + (size_t)blockIdx.y * a.Nc;
   float2* out = a.out + (size_t)blockIdx.y * a.Nc;
   for (int idx = tid; idx < TILE_SEQ * a.N2; idx += CQT_THREADS) {
-    const int n2 = idx % a.N2, k1l = idx / a.N2;
+    const int k1l = a.div_n2.div(idx), n2 = idx - k1l * a.N2;
     const int k1 = k1_0 + k1l;
     float2 v = make_float2(0.f, 0.f);
     if (k1 < a.N1) v = in[(size_t)k1 * a.N2 + n2];
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_analysis(const BandArgs
   const int o = find_octave(a, blockIdx.x);
   const int tile = blockIdx.x - a.tile0[o];
   const int M = a.M[o], S = padded_len(M), TB = a.tb[o];
+  const int mshift = 31 - __clz(M);              // octave sizes are powers of two
   const int b0 = tile * TB;
   const int nb = min(TB, a.binsoct - b0);
   float2* A = reinterpret_cast<float2*>(smem_raw);
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_analysis(const BandArgs
   const float2* X = a.X + (size_t)row * (a.Nc + 1);
 #pragma unroll 4
   for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-    const int bl = idx / M, m = idx - bl * M;
+    const int bl = idx >> mshift, m = idx & (M - 1);
     const int lg = s_lg[bl], half = lg / 2;
     // buffer slot m holds window sample i with (i - half) mod M == m
     int i = m + half;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_analysis(const BandArgs
   const float inv_m = 1.0f / (float)M;
   float2* out = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
   for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-    const int bl = idx / M, m = idx - bl * M;
+    const int bl = idx >> mshift, m = idx & (M - 1);
     const float2 v = res[bl * S + pad16(m)];
     out[(size_t)bl * M + m] = make_float2(v.x * inv_m, -v.y * inv_m);
   }
@@ -275,6 +277,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_synth_bands(const BandA
   const int o = find_octave(a, blockIdx.x);
   const int tile = blockIdx.x - a.tile0[o];
   const int M = a.M[o], S = padded_len(M), TB = a.tb[o];
+  const int mshift = 31 - __clz(M);              // octave sizes are powers of two
   const int b0 = tile * TB;
   const int nb = min(TB, a.binsoct - b0);
   float2* A = reinterpret_cast<float2*>(smem_raw);
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_synth_bands(const BandA
   }
 #pragma unroll 4
   for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-    const int bl = idx / M, m = idx - bl * M;
+    const int bl = idx >> mshift, m = idx & (M - 1);
     A[bl * S + pad16(m)] = in[(size_t)bl * M + m];
   }
   __syncthreads();
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_synth_bands(const BandA
   float2* BS = a.BS + (size_t)row * a.sum_lg;
 #pragma unroll 4
   for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-    const int bl = idx / M, m = idx - bl * M;
+    const int bl = idx >> mshift, m = idx & (M - 1);
     const int lg = s_lg[bl], half = lg / 2;
     int i = m + half;
     if (i >= M) i -= M;
@@ -355,6 +358,7 @@ static inline FftFactors to_dev(const babe_fft_factors& f) {
   FftFactors d;
   d.n = f.n; d.nf = f.nf;
   for (int i = 0; i < MAX_FACTORS; ++i) d.radix[i] = f.radix[i];
+  fill_fastdiv(d);
   return d;
 }
 
@@ -427,6 +431,7 @@ static int big_fft(const babe_cqt_plan* p, const float2* in, float2* tmp, float2
                    int conj_out, cudaStream_t st) {
   PassArgs a{};
   a.Nc = p->Nc; a.N1 = p->f1.n; a.N2 = p->f2.n;
+  a.div_n2 = make_fastdiv(a.N2);
   a.tw_nc = reinterpret_cast<const float2*>(p->tw_nc);
   a.in = in; a.out = tmp; a.f = to_dev(p->f1); a.roots = reinterpret_cast<const float2*>(p->roots1);
   a.conj_out = 0;

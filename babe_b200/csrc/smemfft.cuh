@@ -18,11 +18,36 @@ namespace babe {
 
 constexpr int MAX_FACTORS = 12;
 
+// Division by a small runtime constant as one wide multiply: q / d = (q * M) >> 40 with
+// M = ceil(2^40 / d), exact for q < 2^20 and d < 2^12 (all task counts here are far below).
+struct FastDiv {
+  unsigned long long M;
+  int d;
+  BABE_HD int div(int q) const { return (int)(((unsigned long long)(unsigned)q * M) >> 40); }
+  BABE_HD int mod(int q) const { return q - div(q) * d; }
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  f.M = ((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d;
+  return f;
+}
+
 struct FftFactors {
   int n;
   int nf;
   int radix[MAX_FACTORS];
+  FastDiv div_m[MAX_FACTORS];    // by n / radix[s]
+  FastDiv div_ns[MAX_FACTORS];   // by the product of the radices before stage s
 };
+inline void fill_fastdiv(FftFactors& f) {
+  int ns = 1;
+  for (int s = 0; s < f.nf; ++s) {
+    f.div_m[s] = make_fastdiv(f.n / f.radix[s]);
+    f.div_ns[s] = make_fastdiv(ns);
+    ns *= f.radix[s];
+  }
+}
 
 BABE_HD float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -104,13 +129,13 @@ template <> BABE_HD void butterfly<16>(float (&vr)[16], float (&vi)[16], const f
 // One Stockham stage: radix R, Ns = product of the radices already applied.
 template <int R>
 BABE_HD void stockham_stage(const float2* in, float2* out, int n, int stride, int nseq, int Ns,
-                            const float2* wn, int tid, int nthreads) {
-  const int m = n / R;
-  const int tw_step = n / (Ns * R);
+                            const float2* wn, int tid, int nthreads, FastDiv dm, FastDiv dns) {
+  const int m = dm.d;
+  const int tw_step = m / Ns;
   const int tasks = nseq * m;
   for (int q = tid; q < tasks; q += nthreads) {
-    const int seq = q / m, j = q - seq * m;
-    const int k = j % Ns;
+    const int seq = dm.div(q), j = q - seq * m;
+    const int k = dns.mod(j);
     const float2* src = in + seq * stride;
     float vr[R], vi[R];
 #pragma unroll
@@ -183,18 +208,18 @@ BABE_HD float2* smem_fft(float2* a, float2* b, const FftFactors& f, int stride, 
   for (int s = 0; s < f.nf; ++s) {
     const int r = f.radix[s];
     switch (r) {
-      case 2: stockham_stage<2>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 3: stockham_stage<3>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 4: stockham_stage<4>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 5: stockham_stage<5>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 7: stockham_stage<7>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 8: stockham_stage<8>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 11: stockham_stage<11>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 13: stockham_stage<13>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 16: stockham_stage<16>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 17: stockham_stage<17>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 19: stockham_stage<19>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
-      case 23: stockham_stage<23>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads); break;
+      case 2: stockham_stage<2>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 3: stockham_stage<3>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 4: stockham_stage<4>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 5: stockham_stage<5>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 7: stockham_stage<7>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 8: stockham_stage<8>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 11: stockham_stage<11>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 13: stockham_stage<13>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 16: stockham_stage<16>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 17: stockham_stage<17>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 19: stockham_stage<19>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
+      case 23: stockham_stage<23>(src, dst, f.n, stride, nseq, Ns, wn, tid, nthreads, f.div_m[s], f.div_ns[s]); break;
       default: break;
     }
     Ns *= r;
