@@ -79,10 +79,10 @@ SIGNATURES = {
                            c_void_p]),
     "babe_spectral_filter": (c_int, [POINTER(CqtPlan), c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
-    "babe_cqt_analysis": (c_int, [POINTER(CqtPlan), c_void_p, POINTER(c_void_p), c_int, c_void_p,
-                                  c_void_p, c_void_p, c_size_t, c_void_p]),
-    "babe_cqt_synthesis": (c_int, [POINTER(CqtPlan), POINTER(c_void_p), c_void_p, c_int, c_void_p,
-                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "babe_cqt_analysis": (c_int, [POINTER(CqtPlan), c_void_p, POINTER(c_void_p), c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "babe_cqt_synthesis": (c_int, [POINTER(CqtPlan), POINTER(c_void_p), c_int, c_void_p, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

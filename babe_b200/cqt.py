@@ -212,27 +212,31 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _analysis(plan, x, win, scale):
+def _analysis(plan, x, win, scale, planar=False):
     rows = x.shape[0]
-    outs = [torch.empty((rows, plan.c.binsoct, plan.c.M[o]), dtype=torch.complex64, device=x.device)
-            for o in range(plan.c.numocts)]
+    if planar:
+        outs = [torch.empty((rows, 2, plan.c.binsoct, plan.c.M[o]), dtype=torch.float32, device=x.device)
+                for o in range(plan.c.numocts)]
+    else:
+        outs = [torch.empty((rows, plan.c.binsoct, plan.c.M[o]), dtype=torch.complex64, device=x.device)
+                for o in range(plan.c.numocts)]
     ptrs = (ctypes.c_void_p * plan.c.numocts)(*[o.data_ptr() for o in outs])
     ws, n = plan.workspace(rows)
     # algorithmic bytes: read x, write the complex coefficients
     with profiling.op("cqt_analysis", 4, rows * (4 * plan.c.Ls + 8 * plan.coef_per_row)):
-        check(lib().babe_cqt_analysis(ctypes.byref(plan.c), _p(x), ptrs, rows, _p(win), _p(scale),
+        check(lib().babe_cqt_analysis(ctypes.byref(plan.c), _p(x), ptrs, int(planar), rows, _p(win), _p(scale),
                                       _p(ws), n, _stream()), "cqt_analysis")
     return outs
 
 
-def _synthesis(plan, cs, win, scale):
+def _synthesis(plan, cs, win, scale, planar=False):
     rows = cs[0].shape[0]
     cs = [c.contiguous() for c in cs]
     x = torch.empty((rows, plan.c.Ls), dtype=torch.float32, device=cs[0].device)
     ptrs = (ctypes.c_void_p * plan.c.numocts)(*[c.data_ptr() for c in cs])
     ws, n = plan.workspace(rows)
     with profiling.op("cqt_synthesis", 4, rows * (4 * plan.c.Ls + 8 * plan.coef_per_row)):
-        check(lib().babe_cqt_synthesis(ctypes.byref(plan.c), ptrs, _p(x), rows, _p(win), _p(scale),
+        check(lib().babe_cqt_synthesis(ctypes.byref(plan.c), ptrs, int(planar), _p(x), rows, _p(win), _p(scale),
                                        _p(ws), n, _stream()), "cqt_synthesis")
     return x
 
@@ -274,6 +278,38 @@ class _CqtBwd(torch.autograd.Function):
     def backward(ctx, g):
         plan = ctx.plan
         return (None, *_analysis(plan, g.contiguous(), plan.win_gdMM, plan.scale_bwd_adj))
+
+
+class _CqtFwdPlanar(torch.autograd.Function):
+    """fwd with real (B,2,binsoct,T_o) outputs; the gradient of a real plane pair is the same
+    complex cotangent (dL/dRe + i dL/dIm), so the backward is the planar synthesis with g/M."""
+
+    @staticmethod
+    def forward(ctx, x, plan):
+        ctx.plan, ctx.rows = plan, x.shape[0]
+        return tuple(_analysis(plan, x, plan.win_g, None, planar=True))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gcs):
+        plan = ctx.plan
+        gcs = [g if g is not None else
+               torch.zeros((ctx.rows, 2, plan.c.binsoct, plan.c.M[o]), dtype=torch.float32, device=plan.device)
+               for o, g in enumerate(gcs)]
+        return _synthesis(plan, gcs, plan.win_gM, plan.scale_fwd_adj, planar=True), None
+
+
+class _CqtBwdPlanar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, *cs):
+        ctx.plan = plan
+        return _synthesis(plan, list(cs), plan.win_gdM, None, planar=True)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        plan = ctx.plan
+        return (None, *_analysis(plan, g.contiguous(), plan.win_gdMM, plan.scale_bwd_adj, planar=True))
 
 
 class _SpectralFilter(torch.autograd.Function):
@@ -344,6 +380,21 @@ class CQT_nsgt:
                 raise ValueError(f"octave {o}: shape {tuple(c.shape)}")
             flat.append(c.reshape(-1, self.binsoct, self.size_per_oct[o]).contiguous())
         return _CqtBwd.apply(self.plan, *flat).reshape(*lead, self.Ls)
+
+    def fwd_planar(self, x):
+        """x (B,T) -> list of float32 (B,2,binsoct,T_o): exactly the tensors the denoiser builds from
+        ``fwd`` with view_as_real/permute/contiguous (networks/cqtdiff+.py:750-753), written directly."""
+        return list(_CqtFwdPlanar.apply(self._rows(x), self.plan))
+
+    def bwd_planar(self, cs):
+        """list of float32 (B,2,binsoct,T_o) -> (B,audio_len); replaces the permute/contiguous/
+        view_as_complex of networks/cqtdiff+.py:826-830 followed by ``bwd``."""
+        flat = []
+        for o, c in enumerate(cs):
+            if c.shape[1:] != (2, self.binsoct, self.size_per_oct[o]) or c.dtype != torch.float32 or not c.is_cuda:
+                raise ValueError(f"octave {o}: expected CUDA float32 (B,2,{self.binsoct},{self.size_per_oct[o]})")
+            flat.append(c.contiguous())
+        return _CqtBwdPlanar.apply(self.plan, *flat)
 
     # upstream names
     nsgtf = fwd

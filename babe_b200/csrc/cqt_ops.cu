@@ -208,7 +208,8 @@ struct BandArgs {
   int tile0[BABE_MAX_OCTAVES + 1];       // first work item of octave o
   FftFactors fm[BABE_MAX_OCTAVES];
   const float2* rootsm[BABE_MAX_OCTAVES];
-  float2* coef[BABE_MAX_OCTAVES];        // per-octave coefficient tensors [B, binsoct, M]
+  float2* coef[BABE_MAX_OCTAVES];        // per-octave coefficient tensors [B, binsoct, M] complex
+  int planar;                            // 1: float [B, 2, binsoct, M] (re plane, im plane) instead
   const int* band_p; const int* band_lg; const int* band_off;
   const float* win; const float* scale;
   const float2* X;                       // analysis: half spectrum [B, Nc+1]
@@ -264,11 +265,22 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_analysis(const BandArgs
   __syncthreads();
   const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, BAND_THREADS);
   const float inv_m = 1.0f / (float)M;
-  float2* out = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
-  for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-    const int bl = idx >> mshift, m = idx & (M - 1);
-    const float2 v = res[bl * S + pad16(m)];
-    out[(size_t)bl * M + m] = make_float2(v.x * inv_m, -v.y * inv_m);
+  if (!a.planar) {
+    float2* out = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
+    for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
+      const int bl = idx >> mshift, m = idx & (M - 1);
+      const float2 v = res[bl * S + pad16(m)];
+      out[(size_t)bl * M + m] = make_float2(v.x * inv_m, -v.y * inv_m);
+    }
+  } else {   // the layout the denoiser consumes (networks/cqtdiff+.py:750-753) without the transposing copy
+    float* ore = reinterpret_cast<float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + b0) * M;
+    float* oim = ore + (size_t)a.binsoct * M;
+    for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
+      const int bl = idx >> mshift, m = idx & (M - 1);
+      const float2 v = res[bl * S + pad16(m)];
+      ore[(size_t)bl * M + m] = v.x * inv_m;
+      oim[(size_t)bl * M + m] = -v.y * inv_m;
+    }
   }
 }
 
@@ -291,10 +303,20 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_synth_bands(const BandA
     const int j = o * a.binsoct + b0 + i;
     s_lg[i] = a.band_lg[j]; s_off[i] = a.band_off[j];
   }
+  if (!a.planar) {
 #pragma unroll 4
-  for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-    const int bl = idx >> mshift, m = idx & (M - 1);
-    A[bl * S + pad16(m)] = in[(size_t)bl * M + m];
+    for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
+      const int bl = idx >> mshift, m = idx & (M - 1);
+      A[bl * S + pad16(m)] = in[(size_t)bl * M + m];
+    }
+  } else {
+    const float* ire = reinterpret_cast<const float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + b0) * M;
+    const float* iim = ire + (size_t)a.binsoct * M;
+#pragma unroll 4
+    for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
+      const int bl = idx >> mshift, m = idx & (M - 1);
+      A[bl * S + pad16(m)] = make_float2(ire[(size_t)bl * M + m], iim[(size_t)bl * M + m]);
+    }
   }
   __syncthreads();
   const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, BAND_THREADS);
@@ -535,9 +557,9 @@ extern "C" int babe_spectral_filter(const babe_cqt_plan* plan, const float* x, f
 }
 
 extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
-                                 float* const* out_octaves_host, int B, const float* win,
-                                 const float* bin_scale, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+                                 float* const* out_octaves_host, int planar, int B,
+                                 const float* win, const float* bin_scale, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   int rc = validate_plan(plan, true);
   if (rc) return rc;
   BABE_REQUIRE(x && out_octaves_host && win && B >= 1, BABE_EBADARG, "cqt_analysis: bad arguments");
@@ -561,15 +583,16 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
     BABE_REQUIRE(out_octaves_host[o] != nullptr, BABE_EBADARG, "cqt_analysis: null octave %d", o);
     a.coef[o] = reinterpret_cast<float2*>(out_octaves_host[o]);
   }
-  a.win = win; a.scale = bin_scale; a.X = w.bufX;
+  a.win = win; a.scale = bin_scale; a.X = w.bufX; a.planar = planar ? 1 : 0;
   cudaFuncSetAttribute(k_cqt_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_cqt_analysis<<<dim3(items, B), BAND_THREADS, smem, st>>>(a);
   return check_launch("k_cqt_analysis");
 }
 
 extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const* in_octaves_host,
-                                  float* x, int B, const float* win, const float* bin_scale,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+                                  int planar, float* x, int B, const float* win,
+                                  const float* bin_scale, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   int rc = validate_plan(plan, true);
   if (rc) return rc;
   BABE_REQUIRE(x && in_octaves_host && win && B >= 1, BABE_EBADARG, "cqt_synthesis: bad arguments");
@@ -585,7 +608,7 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
     BABE_REQUIRE(in_octaves_host[o] != nullptr, BABE_EBADARG, "cqt_synthesis: null octave %d", o);
     a.coef[o] = const_cast<float2*>(reinterpret_cast<const float2*>(in_octaves_host[o]));
   }
-  a.win = win; a.scale = nullptr; a.BS = w.bufS;
+  a.win = win; a.scale = nullptr; a.BS = w.bufS; a.planar = planar ? 1 : 0;
   cudaFuncSetAttribute(k_cqt_synth_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_cqt_synth_bands<<<dim3(items, B), BAND_THREADS, smem, st>>>(a);
   rc = check_launch("k_cqt_synth_bands");

@@ -215,14 +215,23 @@ class CQTDiffPlus(nn.Module):
 
     def forward(self, inputs, sigma):
         emb = self.embedding(sigma)
-        octaves = self.CQTransform.fwd(inputs.unsqueeze(1))      # lowest octave first
-        out_octaves = list(octaves)
+        # the CUDA transform emits / consumes the planar (B,2,F,T) layout directly, which removes the
+        # 14 transposing copies per evaluation of networks/cqtdiff+.py:750-753 and :826-830
+        planar = hasattr(self.CQTransform, "fwd_planar")
+        if planar:
+            octaves = self.CQTransform.fwd_planar(inputs)            # lowest octave first
+        else:
+            octaves = self.CQTransform.fwd(inputs.unsqueeze(1))
+        out_octaves = [None] * self.num_octs
         hs = []
         X = pyr = None
         last = self.num_octs - 1
         for i, (init_block, pyr_proj, res_block) in enumerate(self.downs):
             # octave consumed from the top: complex (B,1,F,T) -> planar (B,2,F,T)
-            C = torch.view_as_real(octaves[-1 - i].squeeze(1)).permute(0, 3, 1, 2).contiguous()
+            if planar:
+                C = octaves[-1 - i]
+            else:
+                C = torch.view_as_real(octaves[-1 - i].squeeze(1)).permute(0, 3, 1, 2).contiguous()
             C2 = init_block(C, emb)
             if i == 0:
                 X, pyr = C2, self.downsamplerT(C)
@@ -246,11 +255,17 @@ class CQTDiffPlus(nn.Module):
             Xout = (Xout + out_block(X, emb)) / (2 ** 0.5)
             X = X[:, :, self.bins_per_oct:, :]
             Out, Xout = Xout[:, :, :self.bins_per_oct, :], Xout[:, :, self.bins_per_oct:, :]
-            out_octaves[i] = torch.view_as_complex(Out.permute(0, 2, 3, 1).contiguous()).unsqueeze(1)
+            if planar:
+                out_octaves[i] = Out.contiguous()
+            else:
+                out_octaves[i] = torch.view_as_complex(Out.permute(0, 2, 3, 1).contiguous()).unsqueeze(1)
             if j > 0:
                 X = self.upsamplerT(X)
                 Xout = self.upsamplerT(Xout)
-        pred = self.CQTransform.bwd(out_octaves).squeeze(1)[:, :inputs.shape[-1]]
+        if planar:
+            pred = self.CQTransform.bwd_planar(out_octaves)[:, :inputs.shape[-1]]
+        else:
+            pred = self.CQTransform.bwd(out_octaves).squeeze(1)[:, :inputs.shape[-1]]
         assert pred.shape == inputs.shape, "bad shapes"
         return pred
 

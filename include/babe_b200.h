@@ -193,15 +193,17 @@ int babe_spectral_filter(const babe_cqt_plan* plan, const float* x, float* y, in
 /* Analysis (a16 CQT_nsgt.fwd, and the backward of bwd):
  *   c_j = IFFT_M(fold(rfft(x)[bins of band j] * win[band_off[j]+i] * bin_scale))
  * out_octaves_host: HOST array of numocts DEVICE pointers, octave o receives
- * [B, binsoct, M[o]] complex64 (lowest octave first). */
+ * [B, binsoct, M[o]] complex64 (lowest octave first), or, planar != 0, float
+ * [B, 2, binsoct, M[o]] (real plane, imaginary plane): the layout the denoiser
+ * builds with view_as_real + permute + contiguous at networks/cqtdiff+.py:750-753. */
 int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x, float* const* out_octaves_host,
-                      int B, const float* win, const float* bin_scale, void* workspace,
+                      int planar, int B, const float* win, const float* bin_scale, void* workspace,
                       size_t workspace_bytes, void* stream);
 /* Synthesis (a17 CQT_nsgt.bwd, and the backward of fwd):
  *   x = irfft(bin_scale * sum_j unfold(FFT_M(c_j)) * win[band_off[j]+i]) */
-int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const* in_octaves_host, float* x,
-                       int B, const float* win, const float* bin_scale, void* workspace,
-                       size_t workspace_bytes, void* stream);
+int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const* in_octaves_host, int planar,
+                       float* x, int B, const float* win, const float* bin_scale, void* workspace,
+                       size_t workspace_bytes, void* stream);   /* planar: networks/cqtdiff+.py:826-830 */
 
 #ifdef __cplusplus
 }

@@ -107,3 +107,31 @@ def test_full_batch_properties(CQT):
     d = torch.randn_like(x)
     lhs = sum((torch.view_as_real(ci) * ct).double().sum() for ci, ct in zip(cq.fwd(d), cot))
     assert abs(float(lhs - (gx.double() * d.double()).sum())) < 1e-4 * abs(float(lhs))
+
+
+def test_planar_layout_matches_interleaved(CQT):
+    """a21: (B,2,F,T) float planes written/read directly == view_as_real + permute of the complex API
+    (networks/cqtdiff+.py:750-753, :826-830), forward values and both gradients."""
+    cq = CQT(5, 24, mode="oct", window=("kaiser", 1), fs=44100, audio_len=30030, device="cuda")
+    torch.manual_seed(3)
+    x = torch.randn(3, 30030, device="cuda")
+    c = cq.fwd(x.unsqueeze(1))
+    p = cq.fwd_planar(x)
+    for ci, pi in zip(c, p):
+        ref = torch.view_as_real(ci.squeeze(1)).permute(0, 3, 1, 2).contiguous()
+        assert pi.shape == ref.shape and torch.equal(pi, ref)
+    assert torch.equal(cq.bwd_planar(p), cq.bwd(c).squeeze(1))
+    cots = [torch.randn_like(pi) for pi in p]
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    la = sum((pi * ct).sum() for pi, ct in zip(cq.fwd_planar(xa), cots))
+    lb = sum((torch.view_as_real(ci.squeeze(1)).permute(0, 3, 1, 2) * ct).sum()
+             for ci, ct in zip(cq.fwd(xb.unsqueeze(1)), cots))
+    (ga,), (gb,) = torch.autograd.grad(la, xa), torch.autograd.grad(lb, xb)
+    assert rel_l2(ga.cpu(), gb.cpu()) < 1e-6
+    pa = [pi.clone().requires_grad_(True) for pi in p]
+    r = torch.randn(3, 30030, device="cuda")
+    gpa = torch.autograd.grad((cq.bwd_planar(pa) * r).sum(), pa)
+    ca = [ci.clone().requires_grad_(True) for ci in c]
+    gca = torch.autograd.grad((cq.bwd(ca).squeeze(1) * r).sum(), ca)
+    for gp, gc in zip(gpa, gca):
+        assert rel_l2(gp.cpu(), torch.view_as_real(gc.squeeze(1)).permute(0, 3, 1, 2).cpu()) < 1e-6
