@@ -68,3 +68,71 @@ def test_rid_outputs_and_device_noise(golden):
     s.generator = torch.Generator(device="cuda").manual_seed(3)
     x2, _ = s.predict_blind_bwe(y.clone())
     assert torch.equal(x1, x2)
+
+
+def test_compute_sweep_matches_oracle(golden):
+    """a14 (testing/blind_bwe_sampler.py:598-616): loss and (d/dfc, d/dA) on the 15x12 grid."""
+    from oracle import filter_fit as ofit, stft_filter as osf
+    from babe_b200 import sampler
+    g, y, args, model, s = _setup(golden, max_iter=2)
+    dev = y.device
+    s.freqs = torch.fft.rfftfreq(args.tester.blind_bwe.NFFT, d=1 / args.exp.sample_rate).to(dev)
+    s._fit = sampler.FilterFit.from_args(args, dev)
+    s.fc_s = torch.logspace(2.5, 4, 15).to(dev)
+    s.A_s = torch.linspace(-80, -5, 12).to(dev)
+    xden = torch.from_numpy(g["fit_xden"]).to(dev)
+    norms, grads = s.compute_sweep(xden, y)
+    assert norms.shape == (15, 12) and grads.shape == (15, 12, 2)
+    a, b, c = osf.stft_mag_stats(xden.cpu().double(), y.cpu().double(), int(g["nfft"]))
+    f = ofit.rfft_freqs(int(g["nfft"]), int(g["sr"]), torch.float64)
+    w = osf.freq_weight_vector("sqrt", f.numel()).double()
+    for i, j in ((0, 0), (7, 5), (14, 11)):
+        p = torch.stack((s.fc_s[i].reshape(1), s.A_s[j].reshape(1))).cpu().double()
+        nrm, gr = ofit.loss_and_grad_from_stats(a, b, c, p, f, w)
+        assert abs(float(norms[i, j]) - float(nrm)) < 1e-4 * float(nrm)
+        assert rel_l2(grads[i, j], gr.reshape(-1)) < 1e-3
+
+
+@pytest.mark.parametrize("variant", ["data_consistency", "snr", "smoothl1", "cosine", "stft", "stft_mag",
+                                     "stft_logmag", "sweep_rid"])
+def test_optional_branches_run(golden, variant):
+    """Non-default branches of get_rec_grads / fit_params / the sampling loop
+    (testing/blind_bwe_sampler.py:80-115, 542-548, 704-709): executed on the CUDA operators."""
+    g, y, args, model, s = _setup(golden, max_iter=2)
+    ps = args.tester.posterior_sampling
+    y_in = y.clone()
+    kw = {}
+    if variant == "data_consistency":
+        ps.data_consistency = True
+        s.data_consistency = True
+    elif variant == "snr":
+        ps.SNR_observations = 30
+    elif variant in ("smoothl1", "cosine"):
+        ps.norm = variant
+    elif variant.startswith("stft"):
+        ps.stft_distance.use = True
+        ps.stft_distance.nfft = 1024
+        ps.freq_weighting = "sqrt"
+        ps.stft_distance.mag = variant != "stft"
+        ps.stft_distance.logmag = variant == "stft_logmag"
+    elif variant == "sweep_rid":
+        kw = dict(rid=True, compute_sweep=True)
+    torch.manual_seed(1)
+    out = s.predict_blind_bwe(y_in, max_steps=2, **kw)
+    x = out[0]
+    assert x.shape == y.shape and torch.isfinite(x).all()
+    if variant == "snr":
+        assert not torch.equal(y_in, y)                  # the reference adds noise to y IN PLACE (:86, :548)
+    if variant == "sweep_rid":
+        assert len(out) == 7 and out[5].shape == (4, 15, 12) and out[6].shape == (4, 15, 12, 2)
+
+
+def test_non_blind_and_unconditional(golden):
+    g, y, args, model, s = _setup(golden, max_iter=2)
+    filt = torch.tensor([[1000.0], [-20.0]]).cuda()
+    x = s.predict_bwe(y.clone(), filt, "fc_A")
+    assert x.shape == y.shape and torch.isfinite(x).all()
+    with pytest.raises(NotImplementedError):
+        s.predict_bwe(y.clone(), filt, "firwin")
+    xu = s.predict_unconditional(tuple(y.shape), y.device)
+    assert xu.shape == y.shape and torch.isfinite(xu).all()
