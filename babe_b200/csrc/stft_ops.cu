@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "filter_design.cuh"
 #include "regfft.cuh"
+#include "regfft_packed.cuh"
 
 namespace babe {
 
@@ -159,7 +160,7 @@ struct Core3 {
   __device__ static __forceinline__ void fwd(float (&ar)[16], float (&ai)[16], float (&br)[16],
                                              float (&bi)[16], float2* ex, const float2* tw,
                                              const Regs& rg, int t, int bar) {
-    fft_reg<16>(ar, ai);
+    fft16_split(ar, ai);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1)
       ex[k1 * ROW + t] = make_float2(ar[k1] * rg.wr[k1] - ai[k1] * rg.wi[k1],
@@ -169,7 +170,7 @@ struct Core3 {
       float2* col = ex + (t >> 4) * ROW + (t & 15);          // + 16 n2
 #pragma unroll
       for (int n2 = 0; n2 < 16; ++n2) { const float2 v = col[16 * n2]; br[n2] = v.x; bi[n2] = v.y; }
-      fft_reg<16>(br, bi);
+      fft16_split(br, bi);
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) col[16 * k2] = make_float2(br[k2], bi[k2]);
     }
@@ -182,7 +183,7 @@ struct Core3 {
         const float2 v = cmulf(row[n3].x, row[n3].y, tw[n3 * k2]);
         br[n3] = v.x; bi[n3] = v.y;
       }
-      fft_reg<16>(br, bi);
+      fft16_split(br, bi);
     }
   }
   __device__ static __forceinline__ void inv(float (&br)[16], float (&bi)[16], float (&ar)[16],
@@ -191,7 +192,7 @@ struct Core3 {
     {
       const int k2 = t >> 4;
       float2* row = ex + (t & 15) * ROW + 16 * k2;
-      fft_reg<16>(bi, br);                                    // inverse over k3 -> n3
+      fft16_split(bi, br);                                    // inverse over k3 -> n3
 #pragma unroll
       for (int n3 = 0; n3 < 16; ++n3) row[n3] = cmulcf(br[n3], bi[n3], tw[n3 * k2]);
     }
@@ -200,7 +201,7 @@ struct Core3 {
       float2* col = ex + (t >> 4) * ROW + (t & 15);
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) { const float2 v = col[16 * k2]; br[k2] = v.x; bi[k2] = v.y; }
-      fft_reg<16>(bi, br);                                    // inverse over k2 -> n2
+      fft16_split(bi, br);                                    // inverse over k2 -> n2
 #pragma unroll
       for (int n2 = 0; n2 < 16; ++n2) col[16 * n2] = make_float2(br[n2], bi[n2]);
     }
@@ -211,7 +212,7 @@ struct Core3 {
       ar[k1] = v.x * rg.wr[k1] + v.y * rg.wi[k1];             // * conj(W^{t k1})
       ai[k1] = v.y * rg.wr[k1] - v.x * rg.wi[k1];
     }
-    fft_reg<16>(ai, ar);                                      // inverse over k1 -> n1
+    fft16_split(ai, ar);                                      // inverse over k1 -> n1
   }
   // (pr,pi)[i] <- Z[N - (t + 256 i)]
   __device__ static __forceinline__ void mirror(const float (&br)[16], const float (&bi)[16],
