@@ -263,6 +263,58 @@ def run_ours(a):
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------
+# "library" baseline on the same GPU: the reference's own torch formulation of the operator
+# (torch.stft / torch.istft -> cuFFT, masked index ops, autograd) -- measurement only.
+def torch_apply_filter(x, H, nfft):
+    """utils/blind_bwe_utils.py:6-39 as the reference runs it on a GPU."""
+    window = torch.hamming_window(window_length=nfft).to(x.device)
+    xp = torch.cat((x, torch.zeros(*x.shape[:-1], nfft).to(x.device)), 1)
+    X = torch.stft(xp, nfft, hop_length=nfft // 2, window=window, center=False, onesided=True, return_complex=True)
+    X = X * H.unsqueeze(-1)
+    return torch.istft(X, nfft, hop_length=nfft // 2, window=window, center=False, return_complex=False)[:, :x.shape[-1]]
+
+
+def torch_design_filter(fc, A, f):
+    """utils/blind_bwe_utils.py:82-119 (multi-slope branch)."""
+    H = torch.zeros(f.shape).to(f.device)
+    H[f < fc[0]] = 1
+    H[f >= fc[0]] = 10 ** (A[0] * torch.log2(f[f >= fc[0]] / fc[0]) / 20)
+    for i in range(1, len(fc)):
+        H[f >= fc[i]] = 10 ** (A[i] * torch.log2(f[f >= fc[i]] / fc[i]) / 20) * H[f >= fc[i]][0]
+    return H
+
+
+def torch_fit_loop(xden, y, params, f, nfft, iters=100):
+    """testing/blind_bwe_sampler.py:556-590 as the reference runs it (Python loop, autograd, host syncs)."""
+    window = torch.hamming_window(window_length=nfft).to(y.device)
+
+    def stft(v):
+        vp = torch.cat((v, torch.zeros(*v.shape[:-1], nfft).to(v.device)), 1)
+        return torch.view_as_real(torch.stft(vp, nfft, hop_length=nfft // 2, window=window, center=False,
+                                             onesided=True, return_complex=True))
+    Xd, Y = stft(xden), stft(y)
+    Xm = torch.sqrt(Xd[..., 0] ** 2 + Xd[..., 1] ** 2)
+    Ym = torch.sqrt(Y[..., 0] ** 2 + Y[..., 1] ** 2)
+    w = torch.sqrt(torch.linspace(0, 1, Xm.shape[1]).to(y.device)).unsqueeze(-1)
+    mu = torch.tensor([1000.0, 10.0], device=y.device)
+    p = params.clone()
+    for _ in range(iters):
+        p.requires_grad = True
+        H = torch_design_filter(p[0], p[1], f)
+        norm = torch.linalg.norm((Xm * H.unsqueeze(-1) * w).reshape(-1) - (Ym * w).reshape(-1), ord=2)
+        g = torch.autograd.grad(norm, p, create_graph=True)
+        p = p - mu.unsqueeze(1) * g[0]
+        p.detach_()
+        p[0, 0] = torch.clamp(p[0, 0], min=20, max=SR // 2)
+        for k in range(1, p.shape[1]):
+            p[0, k] = torch.clamp(p[0, k], min=p[0, k - 1] + 1, max=SR // 2)
+        p[1, 0] = torch.clamp(p[1, 0], min=-50, max=-1)
+        for k in range(1, p.shape[1]):
+            p[1, k] = torch.clamp(p[1, k], min=-50, max=p[1, k - 1])
+    return p
+
+
 def operator_probe(device, peak):
     """"operator % of HBM roofline" (second half of BASELINE.json's metric): the streaming
     operators alone at a batch that fills the GPU (config 4: B=512 x T=2^17, NFFT=4096),
@@ -288,6 +340,12 @@ def operator_probe(device, peak):
         "cqt_synthesis_B64": (lambda: cq.bwd(coefs[0]), 64 * (4 * AUDIO_LEN + 8 * cq.plan.coef_per_row)),
         "hpf_DC_B64": (lambda: cq.apply_hpf_DC(xc), 64 * 8 * AUDIO_LEN),
     }
+    Hd = ops.design_filter(fc, A, f, strict=False)
+    x8, y8 = x[:8, :AUDIO_LEN // 2].contiguous(), y[:8, :AUDIO_LEN // 2].contiguous()
+    p0 = torch.tensor([[280.0, 285, 290, 295, 300], [-15.0, -17, -20, -25, -30]], device=device)
+    cases["torch+cuFFT apply_filter (library baseline)"] = (lambda: torch_apply_filter(x, Hd, NFFT), 8 * B * T)
+    cases["torch+cuFFT hpf (rfft/irfft, library baseline) B64"] = (
+        lambda: torch.fft.irfft(torch.fft.rfft(xc) * cq.plan.Hhpf, n=AUDIO_LEN), 64 * 8 * AUDIO_LEN)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     res = {"shape": f"B={B} x T={T} (STFT ops), B=64 x T={AUDIO_LEN} (CQT ops)", "l2": "flushed between iterations"}
     for name, (fn, nbytes) in cases.items():
@@ -305,6 +363,17 @@ def operator_probe(device, peak):
         ms = sorted(ts)[len(ts) // 2]
         gbs = nbytes / 1e9 / (ms / 1e3)
         res[name] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    # filter fit: one launch vs the reference's Python loop on the same GPU (latency, 8 rows)
+    from babe_b200 import sampler as _s
+    fit = _s.FilterFit(nfft=NFFT, sample_rate=SR, device=device)
+    for name, fn in (("fit_params 100 it (stats + 1 launch)", lambda: fit(x8, y8, p0.clone())),
+                     ("torch fit loop 100 it (library baseline)", lambda: torch_fit_loop(x8, y8, p0, f, NFFT))):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        res[name] = {"ms": round((time.perf_counter() - t0) * 1e3, 3)}
     return res
 
 
