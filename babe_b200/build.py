@@ -22,12 +22,23 @@ def _sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+def _source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive the
+    snapshot copy to the GPU box; a spurious rebuild there would cost minutes)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    files.append(os.path.join(ROOT, "include", "babe_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(LIB + ".srchash"):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "babe_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(LIB + ".srchash").read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -56,6 +67,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     cmd = [nvcc, "-shared", *ARCH, "-o", LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
+    with open(LIB + ".srchash", "w") as f:
+        f.write(_source_hash())
     return LIB
 
 
