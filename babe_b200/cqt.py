@@ -341,6 +341,8 @@ class CQT_nsgt:
         if dtype != torch.float32:
             raise NotImplementedError("float32 only")
         device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         if device.type != "cuda":
             raise BabeError(f"CQT_nsgt on {device}: babe_b200 runs on CUDA only (no CPU fallback)")
         if audio_len % 2 != 0:
@@ -356,6 +358,9 @@ class CQT_nsgt:
     def _rows(self, x):
         if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32):
             raise BabeError("CQT_nsgt expects CUDA float32 tensors")
+        if x.device != self.device or x.device.index not in (None, torch.cuda.current_device()):
+            raise BabeError(f"input on {x.device}, plan on {self.device}, current device "
+                            f"cuda:{torch.cuda.current_device()}: they must agree")
         if x.shape[-1] != self.Ls:
             raise ValueError(f"input length {x.shape[-1]} != audio_len {self.Ls}")
         return x.reshape(-1, self.Ls).contiguous()

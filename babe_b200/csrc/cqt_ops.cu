@@ -439,6 +439,7 @@ static size_t ws_bytes(const babe_cqt_plan* p, int B) {
 }
 
 static int carve(const babe_cqt_plan* p, int B, void* ws, size_t bytes, Workspace& w) {
+  BABE_REQUIRE(B <= 65535, BABE_EBADARG, "batch %d > 65535 rows per call (grid.y); split the batch", B);
   BABE_REQUIRE(ws != nullptr && bytes >= ws_bytes(p, B), BABE_EBADARG, "workspace too small (%zu < %zu)",
                bytes, ws_bytes(p, B));
   w.bufA = static_cast<float2*>(ws);

@@ -32,6 +32,9 @@ def _cuda_f32(t, name):
                         "(there is no CPU fallback)")
     if t.dtype != torch.float32:
         raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        raise BabeError(f"{name} is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                        "kernels launch on the current device -- call torch.cuda.set_device first")
     return t.detach().contiguous()
 
 
