@@ -620,12 +620,23 @@ __global__ void k_row_sumsq(const double* item_sumsq, int items_per_row, double*
   row_sumsq[row] += s;
 }
 
-__global__ void k_reduce_stats(const float* partial, int n_partials, int n, double* out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// 32 outputs x 8 slices per CTA: slice s adds partials p = s, s+8, ... in order, the 8 slice
+// sums are combined in a fixed order -> deterministic, 8x the parallelism of one thread per output
+__global__ void __launch_bounds__(256) k_reduce_stats(const float* partial, int n_partials, int n, double* out) {
+  __shared__ double sl[8][33];
+  const int o = threadIdx.x & 31, sidx = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;
   double s = 0.0;
-  for (int p = 0; p < n_partials; ++p) s += (double)partial[(size_t)p * n + i];
-  out[i] = s;
+  if (i < n)
+    for (int p = sidx; p < n_partials; p += 8) s += (double)partial[(size_t)p * n + i];
+  sl[sidx][o] = s;
+  __syncthreads();
+  if (sidx == 0 && i < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sl[k][o];
+    out[i] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -865,7 +876,7 @@ static int launch_stats(StatsArgs a, double* abc, void* ws, size_t ws_bytes, cud
   int rc = check_launch("k_stft_stats");
   if (rc) return rc;
   const int n = 3 * G::F;
-  k_reduce_stats<<<(n + 255) / 256, 256, 0, st>>>(a.partial, grid * GROUPS, n, abc);
+  k_reduce_stats<<<(n + 31) / 32, 256, 0, st>>>(a.partial, grid * GROUPS, n, abc);
   return check_launch("k_reduce_stats");
 }
 
