@@ -65,6 +65,8 @@ SIGNATURES = {
                           c_int, c_void_p, c_void_p]),
     "babe_istft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_void_p, c_int, c_void_p]),
+    "babe_fir_filter": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                c_void_p]),
     "babe_stft_stats_workspace": (c_size_t, [c_int, c_int, c_int]),
     "babe_stft_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

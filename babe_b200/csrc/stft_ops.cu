@@ -810,6 +810,70 @@ __global__ void __launch_bounds__(G::TPF* GROUPS, G::MIN_CTAS) k_istft(const Ist
 }
 
 // ---------------------------------------------------------------------------
+// K5: FIR "same" convolution by overlap-save on the Core3 transform (SURVEY 8f-4:
+// the non-blind baseline predict_bwe("firwin"), testing/blind_bwe_sampler.py:211-218,
+// utils/bandwidth_extension.py:76-95).  torch conv1d is a correlation:
+//   y[n] = sum_k b[k] x[n + k - pl],  pl = (L-1)/2 (left "same" padding).
+// A block of V = N - L + 1 outputs needs N inputs; two consecutive blocks ride one
+// complex transform (real kernel => the packed spectrum is multiplied by the table G
+// without separating them).  G = conj(FFT(b zero padded)) / N is prepared by the
+// host once per filter; the adjoint is the same kernel with the reversed taps.
+// ---------------------------------------------------------------------------
+struct FirArgs {
+  const float* x; float* y; int B, T;
+  const float2* twiddle; const float2* G;
+  int L, pl, V;
+  int pairs_per_row;
+};
+
+template <class G_>
+__global__ void __launch_bounds__(G_::TPF, G_::MIN_CTAS) k_fir_filter(const FirArgs a) {
+  using G = G_;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* ex = tw + G::TW_SMEM;
+  G::load_twiddles(tw, a.twiddle);
+  const int t = threadIdx.x;
+  typename G::Regs regs;
+  G::init_regs(regs, a.twiddle, t);
+  __syncthreads();
+  const long long n_items = (long long)a.B * a.pairs_per_row;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int row = (int)(item / a.pairs_per_row);
+    const long long s = (long long)(item % a.pairs_per_row) * 2 * a.V;     // first output of block A
+    const float* xr = a.x + (size_t)row * a.T;
+    float* yr = a.y + (size_t)row * a.T;
+    float ar[G::NT], ai[G::NT], br[G::NF], bi[G::NF];
+#pragma unroll
+    for (int j = 0; j < G::NT; ++j) {
+      const long long pa = s - a.pl + G::TS * j + t, pb = pa + a.V;
+      ar[j] = (pa >= 0 && pa < a.T) ? __ldg(xr + pa) : 0.f;
+      ai[j] = (pb >= 0 && pb < a.T) ? __ldg(xr + pb) : 0.f;
+    }
+    G::fwd(ar, ai, br, bi, ex, tw, regs, t, 1);
+#pragma unroll
+    for (int i = 0; i < G::NF; ++i) {
+      const float2 g = a.G[t + G::KS * i];
+      const float re = br[i] * g.x - bi[i] * g.y;
+      bi[i] = br[i] * g.y + bi[i] * g.x;
+      br[i] = re;
+    }
+    group_sync<G::TPF>(1);
+    G::inv(br, bi, ar, ai, ex, tw, regs, t, 1);
+#pragma unroll
+    for (int j = 0; j < G::NT; ++j) {
+      const int n = G::TS * j + t;
+      if (n < a.V) {
+        const long long pa = s + n, pb = pa + a.V;
+        if (pa < a.T) yr[pa] = ar[j];
+        if (pb < a.T) yr[pb] = ai[j];
+      }
+    }
+    group_sync<G::TPF>(1);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 template <class G, int GROUPS>
@@ -1031,4 +1095,27 @@ extern "C" int babe_istft(const float* X, float* y, int B, int frames, int nfft,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BABE_DISPATCH_NFFT(nfft, return (launch_istft<G, GR>(a, st)));
   return BABE_EUNSUPPORTED;
+}
+
+extern "C" int babe_fir_filter(const float* x, float* y, int B, int T, const float* twiddle,
+                               const float* G, int L, int pad_left, void* stream) {
+  BABE_REQUIRE(x && y && twiddle && G, BABE_EBADARG, "fir_filter: null pointer");
+  BABE_REQUIRE(B >= 0 && T >= 0, BABE_EBADARG, "fir_filter: bad shape B=%d T=%d", B, T);
+  BABE_REQUIRE(L >= 1 && L <= Core3::N / 2 + 1, BABE_EUNSUPPORTED, "fir_filter: %d taps (max %d)", L,
+               Core3::N / 2 + 1);
+  BABE_REQUIRE(pad_left >= 0 && pad_left < L, BABE_EBADARG, "fir_filter: pad_left=%d", pad_left);
+  if (B == 0 || T == 0) return BABE_OK;
+  FirArgs a{};
+  a.x = x; a.y = y; a.B = B; a.T = T;
+  a.twiddle = reinterpret_cast<const float2*>(twiddle);
+  a.G = reinterpret_cast<const float2*>(G);
+  a.L = L; a.pl = pad_left; a.V = Core3::N - L + 1;
+  const int blocks = (T + a.V - 1) / a.V;
+  a.pairs_per_row = (blocks + 1) / 2;
+  const long long items = (long long)B * a.pairs_per_row;
+  const int grid = (int)std::min<long long>(items, (long long)sm_count() * Core3::MIN_CTAS);
+  const size_t smem = sizeof(float2) * (Core3::TW_SMEM + Core3::EX_ELEMS);
+  cudaFuncSetAttribute(k_fir_filter<Core3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fir_filter<Core3><<<grid, Core3::TPF, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("k_fir_filter");
 }

@@ -222,3 +222,40 @@ def fit_params(abc, w, freqs, params, cfg, return_iters=False):
         check(lib().babe_fit_params(_p(abc), _p(w), _p(freqs), F, _p(params), params.shape[1],
                                     ctypes.byref(cfg), _p(iters), _stream()), "fit_params")
     return (params, iters) if return_iters else params
+
+
+# ---------------------------------------------------------------------------
+_FIR_TABLES = {}
+
+
+def fir_tables(taps, device):
+    """(G_fwd, G_adj, L, pad_left) for a tap vector: spectra of the zero padded taps for the
+    overlap-save kernel (float64 FFT on the host, once per filter)."""
+    b = taps.detach().reshape(-1).to("cpu", torch.float64).numpy()
+    key = (b.tobytes(), str(device))
+    if key not in _FIR_TABLES:
+        N, L = 4096, b.shape[0]
+        if L > N // 2 + 1:
+            raise BabeError(f"FIR with {L} taps: at most {N // 2 + 1} are supported")
+
+        def table(v):
+            g = np.conj(np.fft.fft(np.concatenate((v, np.zeros(N - L))))) / N
+            return torch.from_numpy(np.stack((g.real, g.imag), -1).astype(np.float32)).to(device)
+        _FIR_TABLES[key] = (table(b), table(b[::-1].copy()), L, (L - 1) // 2)
+    return _FIR_TABLES[key]
+
+
+def fir_filter(x, taps, adjoint=False):
+    """torch.nn.functional.conv1d(x[:,None], taps[None,None], padding="same") on x[B,T]
+    (utils/bandwidth_extension.py:76-95), or its transpose wrt x."""
+    x = _cuda_f32(x, "x")
+    if x.dim() != 2:
+        raise ValueError("x must be (B, T)")
+    B, T = x.shape
+    Gf, Ga, L, pl = fir_tables(taps, x.device)
+    _, tw = stft_tables(4096, x.device)
+    y = torch.empty_like(x)
+    with profiling.op("fir_filter", 1, 8 * B * T):
+        check(lib().babe_fir_filter(_p(x), _p(y), B, T, _p(tw), _p(Ga if adjoint else Gf), L,
+                                    (L - 1 - pl) if adjoint else pl, _stream()), "fir_filter")
+    return y

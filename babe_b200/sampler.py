@@ -394,12 +394,14 @@ class BlindSamplerFused:
         """testing/blind_bwe_sampler.py:306-364, the ``fc_A`` branch (known
         parametric filter, no re-estimation).  The classical FIR/IIR observation
         models (utils/bandwidth_extension.py) are outside this path."""
-        if filt_type != "fc_A":
-            raise NotImplementedError(f"filt_type {filt_type!r}: only 'fc_A' runs on the CUDA operator")
+        if filt_type not in ("fc_A", "firwin", "firwin_hpf"):
+            raise NotImplementedError(f"filt_type {filt_type!r}: 'fc_A', 'firwin' and 'firwin_hpf' run on the "
+                                      "CUDA operators; the IIR / resampling models are outside this path")
         args = self.args
         device = ylpf.device
         self.freqs = torch.fft.rfftfreq(args.tester.blind_bwe.NFFT, d=1 / args.exp.sample_rate).to(device)
         params = filt.to(device)
+        fir = filt_type != "fc_A"
         y = ylpf
         shape = y.shape
         if self.start_sigma is None:
@@ -411,10 +413,18 @@ class BlindSamplerFused:
         gamma = self.diff_params.get_gamma(t).to(device)
         t_host = t.cpu()
 
+        def fir_rec_grads(x_den, x_in, t_in):
+            """get_rec_grads (:75-135, norm 2) with the FIR degradation of apply_FIR_filter (:211-218)."""
+            from . import bandwidth_extension as bwe
+            norm = torch.linalg.norm(y - bwe.apply_low_pass_firwin(x_den, params), dim=1, ord=2)
+            (g,) = torch.autograd.grad(outputs=norm.sum(), inputs=x_in)
+            normguide = torch.linalg.norm(g) / args.exp.audio_len ** 0.5
+            return self.xi / (normguide + 1e-6) * g / t_in
+
         def score_fn(x_in, t_in):
             x_in = x_in.detach().requires_grad_(True)
             x_den = self.get_denoised_estimate(x_in, t_in)
-            rec = self.get_rec_grads(x_den, y, x_in, t_in, params)
+            rec = fir_rec_grads(x_den, x_in, t_in) if fir else self.get_rec_grads(x_den, y, x_in, t_in, params)
             x_in = x_in.detach()
             return (x_den.detach() - x_in) / t_in ** 2 - rec
 

@@ -104,6 +104,17 @@ int babe_istft(const float* X, float* y, int B, int frames, int nfft, int out_le
                const float* window, const float* twiddle,
                const float* bin_scale, int out_env_div, void* stream);
 
+/* ---- classical FIR observation model ------------------------- */
+/* Replaces apply_low_pass_firwin (utils/bandwidth_extension.py:76-95) and
+ * BlindSampler.apply_FIR_filter (testing/blind_bwe_sampler.py:211-218):
+ * torch conv1d(padding="same") with L taps, y[n] = sum_k b[k] x[n + k - pad_left],
+ * by overlap-save on the 4096-point transform.  G[4096] (device float2) =
+ * conj(FFT_4096(b zero padded)) / 4096; twiddle = the 4096-th roots of
+ * babe_stft_tables_host(4096).  The adjoint wrt x is the same call with the
+ * reversed taps and pad_left' = L - 1 - pad_left.  L <= 2049. */
+int babe_fir_filter(const float* x, float* y, int B, int T, const float* twiddle, const float* G,
+                    int L, int pad_left, void* stream);
+
 /* ---- fit statistics (a6 collapsed) ------------------ */
 /* mode 0: abc[0..F) = sum|X|^2, abc[F..2F) = sum|X||Y|, abc[2F..3F) = sum|Y|^2
  *         over batch and frames, X = STFT(x), Y = STFT(y);

@@ -191,8 +191,27 @@ def gen_fit_and_sampler():
     print("fit+sampler ok", ps)
 
 
+def gen_fir():
+    """Classical FIR observation model (utils/bandwidth_extension.py:43-95)."""
+    import utils.bandwidth_extension as ref_bwe
+    torch.manual_seed(9)
+    x = piano_like(2, 5000, 22050, 21) + 0.01 * torch.randn(2, 5000)
+    out = {"x": x}
+    for tag, taps in (("lpf500", ref_bwe.get_FIR_lowpass(500, 1000, 1, 22050)),
+                      ("hpf499", ref_bwe.get_FIR_high_pass(500, 1000, 1, 22050))):
+        xg = x.clone().requires_grad_(True)
+        y = ref_bwe.apply_low_pass_firwin(xg, taps)
+        r = torch.randn(y.shape)
+        (gx,) = torch.autograd.grad((y * r).sum(), xg)
+        out["taps_" + tag], out["y_" + tag], out["r_" + tag], out["gx_" + tag] = taps, y, r, gx
+    np.savez_compressed(os.path.join(HERE, "fir.npz"),
+                        **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()})
+    print("fir ok")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     gen_operator(1024, 5000, 2, 3, "n1024")
     gen_operator(4096, 9001, 1, 4, "n4096")
     gen_fit_and_sampler()
+    gen_fir()

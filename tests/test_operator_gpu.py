@@ -245,3 +245,29 @@ def test_full_size_properties(bu, sf, B, T, nfft):
     tot = sum(ops.stft_stats(x[i:i + 1], g[i:i + 1], nfft).cpu() for i in range(min(B, 8)))
     if B <= 8:
         assert rel_l2(abc, tot) < TOL
+
+
+def test_fir_filter_golden_and_properties(golden):
+    """overlap-save FIR kernel vs the reference's conv1d golden, its autograd,
+    and the adjoint identity at a benchmark-size batch."""
+    from babe_b200 import bandwidth_extension as bwe, ops
+    from oracle import fir
+    g = golden("fir.npz")
+    x = cuda(g["x"])
+    for tag in ("lpf500", "hpf499"):
+        taps = cuda(g["taps_" + tag])
+        xg = x.clone().requires_grad_(True)
+        y = bwe.apply_low_pass_firwin(xg, taps)
+        assert rel_l2(y.detach().cpu(), g["y_" + tag]) < TOL
+        (gx,) = torch.autograd.grad((y * cuda(g["r_" + tag])).sum(), xg)
+        assert rel_l2(gx.cpu(), g["gx_" + tag]) < TOL
+    torch.manual_seed(2)
+    taps = cuda(g["taps_lpf500"]).reshape(-1)
+    for B, T in ((1, 1), (3, 3597), (2, 7195), (8, 184184)):
+        xb, gb = torch.randn(B, T, device="cuda"), torch.randn(B, T, device="cuda")
+        yb = ops.fir_filter(xb, taps)
+        if B * T < 30000:
+            assert rel_l2(yb.cpu(), fir.apply_fir_same(xb.cpu(), taps.cpu())) < TOL
+        lhs = (yb.double() * gb.double()).sum()
+        rhs = (xb.double() * ops.fir_filter(gb, taps, adjoint=True).double()).sum()
+        assert abs(float(lhs - rhs)) <= 1e-5 * max(abs(float(lhs)), 1e-3)

@@ -137,3 +137,14 @@ def test_blind_sampler(golden):
     x, p = obs.predict_blind_bwe(cfg, model, model.CQTransform.apply_hpf_DC, y)
     assert rel_l2(p, g["sampler_params"]) < 1e-2
     assert rel_l2(x, g["sampler_x"]) < 1e-2
+
+
+def test_fir_same_padding(golden):
+    """oracle/fir.py against the reference's conv1d(padding='same') (even and odd tap counts)."""
+    from oracle import fir
+    g = golden("fir.npz")
+    x = T(g["x"])
+    for tag in ("lpf500", "hpf499"):
+        taps = T(g["taps_" + tag]).reshape(-1)
+        assert rel_l2(fir.apply_fir_same(x, taps), g["y_" + tag]) < 1e-6
+        assert rel_l2(fir.apply_fir_same_adjoint(T(g["r_" + tag]), taps), g["gx_" + tag]) < 1e-6

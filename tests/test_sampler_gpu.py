@@ -137,7 +137,11 @@ def test_non_blind_and_unconditional(golden):
     filt = torch.tensor([[1000.0], [-20.0]]).cuda()
     x = s.predict_bwe(y.clone(), filt, "fc_A")
     assert x.shape == y.shape and torch.isfinite(x).all()
+    from babe_b200 import bandwidth_extension as bwe
+    taps = bwe.get_FIR_lowpass(500, 1000, 1, 22050).cuda()
+    xf = s.predict_bwe(bwe.apply_low_pass_firwin(y, taps), taps, "firwin")
+    assert xf.shape == y.shape and torch.isfinite(xf).all()
     with pytest.raises(NotImplementedError):
-        s.predict_bwe(y.clone(), filt, "firwin")
+        s.predict_bwe(y.clone(), filt, "cheby1")
     xu = s.predict_unconditional(tuple(y.shape), y.device)
     assert xu.shape == y.shape and torch.isfinite(xu).all()
