@@ -270,4 +270,5 @@ def test_fir_filter_golden_and_properties(golden):
             assert rel_l2(yb.cpu(), fir.apply_fir_same(xb.cpu(), taps.cpu())) < TOL
         lhs = (yb.double() * gb.double()).sum()
         rhs = (xb.double() * ops.fir_filter(gb, taps, adjoint=True).double()).sum()
-        assert abs(float(lhs - rhs)) <= 1e-5 * max(abs(float(lhs)), 1e-3)
+        # <Ax, g> of random vectors is a cancelling sum: compare against its natural scale
+        assert abs(float(lhs - rhs)) <= 1e-6 * float(yb.double().norm() * gb.double().norm()) + 1e-9
