@@ -125,13 +125,16 @@ struct FitArgs {
 };
 
 __global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) {
-  // Per iteration: (1) K threads locate their breakpoints, thread 0 links the
-  // anchors; (2) every thread evaluates its bins: H_k, the loss term and
-  // u_k = (norm dnorm/dH_k) H_k, into shared memory; (3) warp i sums u and
-  // u*log2(f/fc_i) over the bins segment i owns, one more warp sums the loss;
-  // (4) thread 0 applies the chain rule through the anchors, the fp32 gradient
-  // step, the sequential clamps and the stopping test.  All sums run in a fixed
-  // order (bitwise reproducible).
+  // Per iteration (2 CTA barriers):
+  //  (A) every thread evaluates its bins: H_k, the loss term and u_k = (norm dnorm/dH_k) H_k, into
+  //      shared memory;
+  //  (B) warp (q, s) sums quantity q (segment q's u and u*log2(f/fc_q), or the loss) over bin slice s,
+  //      so that all 16 warps work;
+  //  (C) warp 0 alone: lane j applies the chain rule through the anchors for breakpoint j, lane 0
+  //      takes the fp32 gradient step, the sequential clamps and the stopping test
+  //      (testing/blind_bwe_sampler.py:569-588), lanes < K re-locate their breakpoints, lane 0 links
+  //      the anchors for the next iteration -- warp-synchronous, no CTA barrier in between.
+  // All sums run in a fixed order (bitwise reproducible).
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int F = a.F, K = a.K;
   double* sa = reinterpret_cast<double*>(smem_raw);            // w^2 a
@@ -144,11 +147,14 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) 
   __shared__ FilterSegs segs;
   __shared__ float fkf[KMAX];
   __shared__ double scratch[FIT_WARPS];
-  __shared__ double red[2 * KMAX + 1];
+  __shared__ double red[FIT_WARPS + KMAX + 1][2];
+  __shared__ double gsum[2 * KMAX + 1];                        // s-sums, l-sums, loss at [2 KMAX]
   __shared__ float cur[2 * KMAX], prev[2 * KMAX];
   __shared__ int stop_flag;
   __shared__ double c_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NQ = K + 1;                                        // K segments + the loss
+  const int NS = FIT_WARPS / NQ > 0 ? FIT_WARPS / NQ : 1;      // bin slices per quantity
 
   {
     double v = 0.0;
@@ -170,12 +176,11 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) 
       stop_flag = 0;
     }
   }
-  __syncthreads();
+  build_segments_coop(segs, fkf, cur, cur + KMAX, K, sf, F);    // ends with a CTA barrier
 
   int it = 0;
   for (int iter = 0; iter < a.cfg.max_iter; ++iter) {
-    build_segments_coop(segs, fkf, cur, cur + KMAX, K, sf, F);          // (1)
-    for (int k = threadIdx.x; k < F; k += blockDim.x) {                 // (2)
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {                 // (A)
       const float fk = sf[k];
       const int o = bin_owner(segs, k);
       const double h = (double)bin_gain(segs, k, fk);
@@ -189,53 +194,99 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) 
       su[k] = u; sl[k] = l; sown[k] = (signed char)o;
     }
     __syncthreads();
-    for (int q = warp; q <= K; q += FIT_WARPS) {                        // (3)
+    for (int job = warp; job < NQ * NS; job += FIT_WARPS) {             // (B)
+      const int q = job / NS, s = job - q * NS;
+      const int k0 = (int)(((long long)F * s) / NS), k1 = (int)(((long long)F * (s + 1)) / NS);
       double s0 = 0.0, s1 = 0.0;
       if (q < K) {
-        for (int k = lane; k < F; k += 32)
+        for (int k = k0 + lane; k < k1; k += 32)
           if (sown[k] == q) { s0 += su[k]; s1 += sl[k]; }
       } else {
-        for (int k = lane; k < F; k += 32) s0 += ss[k];
+        for (int k = k0 + lane; k < k1; k += 32) s0 += ss[k];
       }
       s0 = warp_sum(s0); s1 = warp_sum(s1);
-      if (lane == 0) {
-        if (q < K) { red[q] = s0; red[KMAX + q] = s1; } else { red[2 * KMAX] = s0; }
-      }
+      if (lane == 0) { red[job][0] = s0; red[job][1] = s1; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {                                             // (4)
-      double gfc[KMAX], gA[KMAX];
-      finish_param_grads(segs, sf, F, red, red + KMAX, gfc, gA);
-      const double S = red[2 * KMAX] + c_total;
-      const double inv_norm = 1.0 / sqrt(S > 0.0 ? S : 0.0);
-      // gradient step in fp32 like the reference (:569), then the clamps (:576-583)
-      for (int i = 0; i < K; ++i) {
-        const float g0 = (float)(gfc[i] * inv_norm), g1 = (float)(gA[i] * inv_norm);
-        cur[i] = __fsub_rn(cur[i], __fmul_rn(a.cfg.mu_fc, g0));
-        cur[KMAX + i] = __fsub_rn(cur[KMAX + i], __fmul_rn(a.cfg.mu_A, g1));
+    if (warp == 0) {                                                    // (C)
+      if (lane <= K) {                                                  // slice partials, fixed order
+        double t0 = 0.0, t1 = 0.0;
+        for (int s = 0; s < NS; ++s) { t0 += red[lane * NS + s][0]; t1 += red[lane * NS + s][1]; }
+        if (lane < K) { gsum[lane] = t0; gsum[KMAX + lane] = t1; } else { gsum[2 * KMAX] = t0; }
       }
-      if (a.cfg.clamp_fc) {
-        cur[0] = fminf(fmaxf(cur[0], a.cfg.fcmin), a.cfg.fcmax);
-        for (int k = 1; k < K; ++k)
-          cur[k] = fminf(fmaxf(cur[k], __fadd_rn(cur[k - 1], 1.0f)), a.cfg.fcmax);
+      __syncwarp();
+      const double alpha = 0.11512925464970229, ln2 = 0.6931471805599453;
+      double gfc = 0.0, gA = 0.0;
+      if (lane < K) {
+        // dL/dA_j, dL/dfc_j: own segment plus every segment whose anchor chain passes through j
+        const int j = lane;
+        double ssum = 0.0;
+        for (int i = 0; i < K; ++i) {
+          if (segs.kf[i] >= F) continue;
+          if (i == j) { ssum += gsum[i]; gA += alpha * gsum[KMAX + i]; continue; }
+          int c = i;                                  // walk i's ancestors; c = child of j on the path
+          while (segs.parent[c] >= 0 && segs.parent[c] != j) c = segs.parent[c];
+          if (segs.parent[c] == j) {
+            ssum += gsum[i];
+            gA += alpha * (double)log2f(__fdiv_rn(sf[segs.kf[c]], segs.fc[j])) * gsum[i];
+          }
+        }
+        gfc = -alpha * (double)segs.A[j] / ((double)segs.fc[j] * ln2) * ssum;
+        const double S = gsum[2 * KMAX] + c_total;
+        const double inv_norm = 1.0 / sqrt(S > 0.0 ? S : 0.0);
+        // gradient step in fp32 like the reference (:569)
+        cur[j] = __fsub_rn(cur[j], __fmul_rn(a.cfg.mu_fc, (float)(gfc * inv_norm)));
+        cur[KMAX + j] = __fsub_rn(cur[KMAX + j], __fmul_rn(a.cfg.mu_A, (float)(gA * inv_norm)));
       }
-      if (a.cfg.clamp_A) {
-        const float top0 = a.cfg.only_negative_A ? -1.0f : a.cfg.Amax;
-        cur[KMAX] = fminf(fmaxf(cur[KMAX], a.cfg.Amin), top0);
-        for (int k = 1; k < K; ++k) {
-          const float top = a.cfg.only_negative_A ? cur[KMAX + k - 1] : a.cfg.Amax;
-          cur[KMAX + k] = fminf(fmaxf(cur[KMAX + k], a.cfg.Amin), top);
+      __syncwarp();
+      if (lane == 0) {                                                  // sequential clamps (:576-583)
+        if (a.cfg.clamp_fc) {
+          cur[0] = fminf(fmaxf(cur[0], a.cfg.fcmin), a.cfg.fcmax);
+          for (int k = 1; k < K; ++k)
+            cur[k] = fminf(fmaxf(cur[k], __fadd_rn(cur[k - 1], 1.0f)), a.cfg.fcmax);
+        }
+        if (a.cfg.clamp_A) {
+          const float top0 = a.cfg.only_negative_A ? -1.0f : a.cfg.Amax;
+          cur[KMAX] = fminf(fmaxf(cur[KMAX], a.cfg.Amin), top0);
+          for (int k = 1; k < K; ++k) {
+            const float top = a.cfg.only_negative_A ? cur[KMAX + k - 1] : a.cfg.Amax;
+            cur[KMAX + k] = fminf(fmaxf(cur[KMAX + k], a.cfg.Amin), top);
+          }
+        }
+        if (iter > 0) {
+          float d0 = 0.f, d1 = 0.f;
+          for (int k = 0; k < K; ++k) {
+            d0 += fabsf(cur[k] - prev[k]);
+            d1 += fabsf(cur[KMAX + k] - prev[KMAX + k]);
+          }
+          if (d0 / (float)K < a.cfg.tol_fc && d1 / (float)K < a.cfg.tol_A) stop_flag = 1;
+        }
+        for (int k = 0; k < K; ++k) { prev[k] = cur[k]; prev[KMAX + k] = cur[KMAX + k]; }
+      }
+      __syncwarp();
+      // segments of the next iterate (warp-synchronous version of build_segments_coop)
+      if (lane < K) {
+        const float c = cur[lane];
+        segs.fc[lane] = c;
+        segs.A[lane] = cur[KMAX + lane];
+        const int k = first_bin_ge(sf, F, c);
+        segs.kf[lane] = k;
+        fkf[lane] = (k < F) ? sf[k] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        segs.K = K;
+        segs.bad = 0;
+        for (int i = 0; i < K; ++i) {
+          int p = -1;
+          for (int j = 0; j < i; ++j)
+            if (segs.kf[j] <= segs.kf[i]) p = j;
+          segs.parent[i] = p;
+          if (i > 0 && segs.kf[i] >= F) { segs.bad = 1; segs.anchor[i] = 1.0f; continue; }
+          segs.anchor[i] = (i == 0 || p < 0) ? 1.0f
+                                             : __fmul_rn(seg_gain(segs.A[p], segs.fc[p], fkf[i]), segs.anchor[p]);
         }
       }
-      if (iter > 0) {
-        float d0 = 0.f, d1 = 0.f;
-        for (int k = 0; k < K; ++k) {
-          d0 += fabsf(cur[k] - prev[k]);
-          d1 += fabsf(cur[KMAX + k] - prev[KMAX + k]);
-        }
-        if (d0 / (float)K < a.cfg.tol_fc && d1 / (float)K < a.cfg.tol_A) stop_flag = 1;
-      }
-      for (int k = 0; k < K; ++k) { prev[k] = cur[k]; prev[KMAX + k] = cur[KMAX + k]; }
     }
     __syncthreads();
     it = iter + 1;
