@@ -18,13 +18,14 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "bandfft.cuh"
 #include "smemfft.cuh"
 
 namespace babe {
 
 constexpr int CQT_THREADS = 256;
 constexpr int MAX_TB = 64;          // bands per CTA (tb <= 2048 / 32)
-constexpr int BAND_THREADS = 128;   // band kernels: 2048-point tiles -> 128 radix-16 tasks per stage
+constexpr int BAND_THREADS = 256;   // band kernels: 16 points per thread, 4096-point tiles (bandfft.cuh)
 constexpr int TILE_SEQ = 8;          // sequences per CTA in the two big-FFT passes
 constexpr int TW_LO = 1024;          // low part of the two-level twiddle tables
 
@@ -210,6 +211,7 @@ struct BandArgs {
   const float2* rootsm[BABE_MAX_OCTAVES];
   float2* coef[BABE_MAX_OCTAVES];        // per-octave coefficient tensors [B, binsoct, M] complex
   int planar;                            // 1: float [B, 2, binsoct, M] (re plane, im plane) instead
+  int B, rows_per_cta;
   const int* band_p; const int* band_lg; const int* band_off;
   const float* win; const float* scale;
   const float2* X;                       // analysis: half spectrum [B, Nc+1]
@@ -222,10 +224,102 @@ __device__ __forceinline__ int find_octave(const BandArgs& a, int item) {
   return o;
 }
 
-__global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_analysis(const BandArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int o = find_octave(a, blockIdx.x);
-  const int tile = blockIdx.x - a.tile0[o];
+// --- octaves with M = 256 * R3: register FFT (bandfft.cuh), 16 / R3 bands per CTA ----------
+template <int R3, bool SYNTH>
+__device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int tile, unsigned char* smem_raw) {
+  using C = BandCore<R3>;
+  constexpr int NB = BAND_THREADS / C::TPB, M = C::M;
+  float2* exs = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = exs + NB * C::EX;
+  const int tid = threadIdx.x, bl = tid / C::TPB, t = tid % C::TPB;
+  const float2* roots_m = a.rootsm[o];
+  C::load_twiddles(tw, roots_m);
+  typename C::Regs rg;
+  C::init_regs(rg, roots_m, t);
+  const int band = tile * NB + bl;
+  const bool active = band < a.binsoct;
+  int p = 0, lg = 0, off = 0;
+  if (active) {
+    const int j = o * a.binsoct + band;
+    p = a.band_p[j]; lg = a.band_lg[j]; off = a.band_off[j];
+  }
+  const int half = lg / 2;
+  float2* ex = exs + bl * C::EX;
+  const float inv_m = 1.0f / (float)M;
+  __syncthreads();
+  const int row_end = min(a.B, (int)(blockIdx.y + 1) * a.rows_per_cta);
+  for (int row = blockIdx.y * a.rows_per_cta; row < row_end; ++row) {
+    float re[16], im[16];
+    if (!SYNTH) {
+      // slot m holds window sample i with (i - half) mod M == m, conjugated (inverse FFT via forward)
+      const float2* X = a.X + (size_t)row * (a.Nc + 1);
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        int i = C::TPB * n1 + t + half;
+        if (i >= M) i -= M;
+        float2 v = make_float2(0.f, 0.f);
+        if (i < lg) {
+          const int k = p - half + i;
+          if (k >= 0 && k <= a.Nc) {
+            float w = a.win[off + i];
+            if (a.scale) w *= a.scale[k];
+            const float2 xv = X[k];
+            v = make_float2(xv.x * w, -xv.y * w);
+          }
+        }
+        re[n1] = v.x; im[n1] = v.y;
+      }
+    } else if (active) {
+      if (!a.planar) {
+        const float2* in = a.coef[o] + ((size_t)row * a.binsoct + band) * M;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) { const float2 v = in[C::TPB * n1 + t]; re[n1] = v.x; im[n1] = v.y; }
+      } else {
+        const float* ire = reinterpret_cast<const float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + band) * M;
+        const float* iim = ire + (size_t)a.binsoct * M;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) { re[n1] = ire[C::TPB * n1 + t]; im[n1] = iim[C::TPB * n1 + t]; }
+      }
+    } else {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) { re[n1] = 0.f; im[n1] = 0.f; }
+    }
+    C::fwd(re, im, ex, tw, rg, t);
+    if (active) {
+      if (!SYNTH) {
+        if (!a.planar) {
+          float2* out = a.coef[o] + ((size_t)row * a.binsoct + band) * M;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) out[C::out_slot(r, t)] = make_float2(re[r] * inv_m, -im[r] * inv_m);
+        } else {   // the layout the denoiser consumes (networks/cqtdiff+.py:750-753) without the transposing copy
+          float* ore = reinterpret_cast<float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + band) * M;
+          float* oim = ore + (size_t)a.binsoct * M;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            ore[C::out_slot(r, t)] = re[r] * inv_m;
+            oim[C::out_slot(r, t)] = -im[r] * inv_m;
+          }
+        }
+      } else {
+        float2* BS = a.BS + (size_t)row * a.sum_lg + off;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          int i = C::out_slot(r, t) + half;
+          if (i >= M) i -= M;
+          if (i < lg) {
+            const float w = a.win[off + i];
+            BS[i] = make_float2(re[r] * w, im[r] * w);
+          }
+        }
+      }
+    }
+    __syncthreads();                             // ex is reused by the next row
+  }
+}
+
+// --- other octave sizes (M < 256): mixed-radix Stockham in shared memory ---------------------
+template <bool SYNTH>
+__device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int tile, unsigned char* smem_raw) {
   const int M = a.M[o], S = padded_len(M), TB = a.tb[o];
   const int mshift = 31 - __clz(M);              // octave sizes are powers of two
   const int b0 = tile * TB;
@@ -233,107 +327,112 @@ __global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_analysis(const BandArgs
   float2* A = reinterpret_cast<float2*>(smem_raw);
   float2* Bf = A + TB * S;
   float2* roots = Bf + TB * S;
-  const int tid = threadIdx.x, row = blockIdx.y;
-  for (int i = tid; i < M; i += BAND_THREADS) roots[i] = a.rootsm[o][i];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < M; i += nthr) roots[i] = a.rootsm[o][i];
   // band descriptors once per CTA (they would otherwise be chains of dependent global loads)
   __shared__ int s_p[MAX_TB], s_lg[MAX_TB], s_off[MAX_TB];
-  for (int i = tid; i < nb; i += BAND_THREADS) {
+  for (int i = tid; i < nb; i += nthr) {
     const int j = o * a.binsoct + b0 + i;
     s_p[i] = a.band_p[j]; s_lg[i] = a.band_lg[j]; s_off[i] = a.band_off[j];
   }
   __syncthreads();
-  const float2* X = a.X + (size_t)row * (a.Nc + 1);
+  const float inv_m = 1.0f / (float)M;
+  const int row_end = min(a.B, (int)(blockIdx.y + 1) * a.rows_per_cta);
+  for (int row = blockIdx.y * a.rows_per_cta; row < row_end; ++row) {
+    if (!SYNTH) {
+      const float2* X = a.X + (size_t)row * (a.Nc + 1);
 #pragma unroll 4
-  for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-    const int bl = idx >> mshift, m = idx & (M - 1);
-    const int lg = s_lg[bl], half = lg / 2;
-    // buffer slot m holds window sample i with (i - half) mod M == m
-    int i = m + half;
-    if (i >= M) i -= M;
-    float2 v = make_float2(0.f, 0.f);
-    if (i < lg) {
-      const int k = s_p[bl] - half + i;
-      if (k >= 0 && k <= a.Nc) {
-        float w = a.win[s_off[bl] + i];
-        if (a.scale) w *= a.scale[k];
-        const float2 xv = X[k];
-        v = make_float2(xv.x * w, -xv.y * w);      // conjugate: inverse FFT via forward
+      for (int idx = tid; idx < nb * M; idx += nthr) {
+        const int bl = idx >> mshift, m = idx & (M - 1);
+        const int lg = s_lg[bl], half = lg / 2;
+        int i = m + half;
+        if (i >= M) i -= M;
+        float2 v = make_float2(0.f, 0.f);
+        if (i < lg) {
+          const int k = s_p[bl] - half + i;
+          if (k >= 0 && k <= a.Nc) {
+            float w = a.win[s_off[bl] + i];
+            if (a.scale) w *= a.scale[k];
+            const float2 xv = X[k];
+            v = make_float2(xv.x * w, -xv.y * w);      // conjugate: inverse FFT via forward
+          }
+        }
+        A[bl * S + pad16(m)] = v;
+      }
+    } else if (!a.planar) {
+      const float2* in = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
+#pragma unroll 4
+      for (int idx = tid; idx < nb * M; idx += nthr) {
+        const int bl = idx >> mshift, m = idx & (M - 1);
+        A[bl * S + pad16(m)] = in[(size_t)bl * M + m];
+      }
+    } else {
+      const float* ire = reinterpret_cast<const float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + b0) * M;
+      const float* iim = ire + (size_t)a.binsoct * M;
+#pragma unroll 4
+      for (int idx = tid; idx < nb * M; idx += nthr) {
+        const int bl = idx >> mshift, m = idx & (M - 1);
+        A[bl * S + pad16(m)] = make_float2(ire[(size_t)bl * M + m], iim[(size_t)bl * M + m]);
       }
     }
-    A[bl * S + pad16(m)] = v;
-  }
-  __syncthreads();
-  const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, BAND_THREADS);
-  const float inv_m = 1.0f / (float)M;
-  if (!a.planar) {
-    float2* out = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
-    for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-      const int bl = idx >> mshift, m = idx & (M - 1);
-      const float2 v = res[bl * S + pad16(m)];
-      out[(size_t)bl * M + m] = make_float2(v.x * inv_m, -v.y * inv_m);
+    __syncthreads();
+    const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, nthr);
+    if (!SYNTH) {
+      if (!a.planar) {
+        float2* out = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
+        for (int idx = tid; idx < nb * M; idx += nthr) {
+          const int bl = idx >> mshift, m = idx & (M - 1);
+          const float2 v = res[bl * S + pad16(m)];
+          out[(size_t)bl * M + m] = make_float2(v.x * inv_m, -v.y * inv_m);
+        }
+      } else {
+        float* ore = reinterpret_cast<float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + b0) * M;
+        float* oim = ore + (size_t)a.binsoct * M;
+        for (int idx = tid; idx < nb * M; idx += nthr) {
+          const int bl = idx >> mshift, m = idx & (M - 1);
+          const float2 v = res[bl * S + pad16(m)];
+          ore[(size_t)bl * M + m] = v.x * inv_m;
+          oim[(size_t)bl * M + m] = -v.y * inv_m;
+        }
+      }
+    } else {
+      float2* BS = a.BS + (size_t)row * a.sum_lg;
+#pragma unroll 4
+      for (int idx = tid; idx < nb * M; idx += nthr) {
+        const int bl = idx >> mshift, m = idx & (M - 1);
+        const int lg = s_lg[bl], half = lg / 2;
+        int i = m + half;
+        if (i >= M) i -= M;
+        if (i < lg) {
+          const float w = a.win[s_off[bl] + i];
+          const float2 v = res[bl * S + pad16(m)];
+          BS[s_off[bl] + i] = make_float2(v.x * w, v.y * w);
+        }
+      }
     }
-  } else {   // the layout the denoiser consumes (networks/cqtdiff+.py:750-753) without the transposing copy
-    float* ore = reinterpret_cast<float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + b0) * M;
-    float* oim = ore + (size_t)a.binsoct * M;
-    for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-      const int bl = idx >> mshift, m = idx & (M - 1);
-      const float2 v = res[bl * S + pad16(m)];
-      ore[(size_t)bl * M + m] = v.x * inv_m;
-      oim[(size_t)bl * M + m] = -v.y * inv_m;
-    }
+    __syncthreads();                             // A / Bf are reused by the next row
   }
 }
 
-__global__ void __launch_bounds__(BAND_THREADS, 6) k_cqt_synth_bands(const BandArgs a) {
+template <bool SYNTH>
+__device__ __forceinline__ void band_tile(const BandArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
   const int tile = blockIdx.x - a.tile0[o];
-  const int M = a.M[o], S = padded_len(M), TB = a.tb[o];
-  const int mshift = 31 - __clz(M);              // octave sizes are powers of two
-  const int b0 = tile * TB;
-  const int nb = min(TB, a.binsoct - b0);
-  float2* A = reinterpret_cast<float2*>(smem_raw);
-  float2* Bf = A + TB * S;
-  float2* roots = Bf + TB * S;
-  const int tid = threadIdx.x, row = blockIdx.y;
-  for (int i = tid; i < M; i += BAND_THREADS) roots[i] = a.rootsm[o][i];
-  const float2* in = a.coef[o] + ((size_t)row * a.binsoct + b0) * M;
-  __shared__ int s_lg[MAX_TB], s_off[MAX_TB];
-  for (int i = tid; i < nb; i += BAND_THREADS) {
-    const int j = o * a.binsoct + b0 + i;
-    s_lg[i] = a.band_lg[j]; s_off[i] = a.band_off[j];
-  }
-  if (!a.planar) {
-#pragma unroll 4
-    for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-      const int bl = idx >> mshift, m = idx & (M - 1);
-      A[bl * S + pad16(m)] = in[(size_t)bl * M + m];
-    }
-  } else {
-    const float* ire = reinterpret_cast<const float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + b0) * M;
-    const float* iim = ire + (size_t)a.binsoct * M;
-#pragma unroll 4
-    for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-      const int bl = idx >> mshift, m = idx & (M - 1);
-      A[bl * S + pad16(m)] = make_float2(ire[(size_t)bl * M + m], iim[(size_t)bl * M + m]);
-    }
-  }
-  __syncthreads();
-  const float2* res = smem_fft(A, Bf, a.fm[o], S, nb, roots, tid, BAND_THREADS);
-  float2* BS = a.BS + (size_t)row * a.sum_lg;
-#pragma unroll 4
-  for (int idx = tid; idx < nb * M; idx += BAND_THREADS) {
-    const int bl = idx >> mshift, m = idx & (M - 1);
-    const int lg = s_lg[bl], half = lg / 2;
-    int i = m + half;
-    if (i >= M) i -= M;
-    if (i < lg) {
-      const float w = a.win[s_off[bl] + i];
-      const float2 v = res[bl * S + pad16(m)];
-      BS[s_off[bl] + i] = make_float2(v.x * w, v.y * w);
-    }
+  switch (a.M[o]) {
+    case 256: band_tile_fast<1, SYNTH>(a, o, tile, smem_raw); break;
+    case 512: band_tile_fast<2, SYNTH>(a, o, tile, smem_raw); break;
+    case 1024: band_tile_fast<4, SYNTH>(a, o, tile, smem_raw); break;
+    case 2048: band_tile_fast<8, SYNTH>(a, o, tile, smem_raw); break;
+    case 4096: band_tile_fast<16, SYNTH>(a, o, tile, smem_raw); break;
+    default: band_tile_generic<SYNTH>(a, o, tile, smem_raw); break;
   }
 }
+
+// analysis: window multiply + fold + per-band inverse FFT of the half spectrum X
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_analysis(const BandArgs a) { band_tile<false>(a); }
+// synthesis, first half: per-band FFT of the coefficients, dual-window multiply -> band spectra BS
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_synth_bands(const BandArgs a) { band_tile<true>(a); }
 
 // overlap-add of the band spectra as a gather, fused with the c2r pre-processing
 struct GatherArgs {
@@ -471,21 +570,39 @@ static int big_fft(const babe_cqt_plan* p, const float2* in, float2* tmp, float2
   return check_launch("k_fft_rows");
 }
 
-static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int& items) {
+static inline int band_r3(int M) {     // M = 256 * R3 handled by BandCore<R3>, else 0
+  switch (M) { case 256: return 1; case 512: return 2; case 1024: return 4; case 2048: return 8;
+               case 4096: return 16; default: return 0; }
+}
+
+static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int& items, int B) {
   a.Nc = p->Nc; a.numocts = p->numocts; a.binsoct = p->binsoct; a.sum_lg = p->sum_lg;
   a.band_p = p->band_p; a.band_lg = p->band_lg; a.band_off = p->band_off;
   smem = 0;
   items = 0;
   for (int o = 0; o < p->numocts; ++o) {
     const int M = p->M[o];
-    int tb = std::max(1, std::min(std::min(p->binsoct, MAX_TB), 2048 / M));   // <= 2048 points per CTA: more, smaller CTAs
+    const int r3 = band_r3(M);
+    int tb;
+    size_t need;
+    if (r3) {                                  // register FFT: 4096 points per CTA
+      tb = 16 / r3;
+      need = sizeof(float2) * ((size_t)tb * 16 * (16 * r3 + 1) + 16 * r3);
+    } else {                                   // shared-memory Stockham: <= 2048 points per CTA
+      tb = std::max(1, std::min(std::min(p->binsoct, MAX_TB), 2048 / M));
+      need = sizeof(float2) * ((size_t)2 * tb * odd_stride(M) + M);
+    }
     a.M[o] = M; a.tb[o] = tb; a.tile0[o] = items;
     a.fm[o] = to_dev(p->fm[o]);
     a.rootsm[o] = reinterpret_cast<const float2*>(p->rootsm[o]);
     items += (p->binsoct + tb - 1) / tb;
-    smem = std::max(smem, sizeof(float2) * ((size_t)2 * tb * odd_stride(M) + M));
+    smem = std::max(smem, need);
   }
   a.tile0[p->numocts] = items;
+  // rows per CTA: keep >= ~4 CTAs per SM in flight, amortise the per-CTA twiddle loads beyond that
+  int rpc = 1;
+  while (rpc < 8 && (long long)items * ((B + 2 * rpc - 1) / (2 * rpc)) >= 4LL * 148) rpc *= 2;
+  a.B = B; a.rows_per_cta = rpc;
   return BABE_OK;
 }
 
@@ -579,14 +696,14 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
   BandArgs a{};
   size_t smem;
   int items;
-  fill_band_args(plan, a, smem, items);
+  fill_band_args(plan, a, smem, items, B);
   for (int o = 0; o < plan->numocts; ++o) {
     BABE_REQUIRE(out_octaves_host[o] != nullptr, BABE_EBADARG, "cqt_analysis: null octave %d", o);
     a.coef[o] = reinterpret_cast<float2*>(out_octaves_host[o]);
   }
   a.win = win; a.scale = bin_scale; a.X = w.bufX; a.planar = planar ? 1 : 0;
   cudaFuncSetAttribute(k_cqt_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_cqt_analysis<<<dim3(items, B), BAND_THREADS, smem, st>>>(a);
+  k_cqt_analysis<<<dim3(items, (B + a.rows_per_cta - 1) / a.rows_per_cta), BAND_THREADS, smem, st>>>(a);
   return check_launch("k_cqt_analysis");
 }
 
@@ -604,14 +721,14 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
   BandArgs a{};
   size_t smem;
   int items;
-  fill_band_args(plan, a, smem, items);
+  fill_band_args(plan, a, smem, items, B);
   for (int o = 0; o < plan->numocts; ++o) {
     BABE_REQUIRE(in_octaves_host[o] != nullptr, BABE_EBADARG, "cqt_synthesis: null octave %d", o);
     a.coef[o] = const_cast<float2*>(reinterpret_cast<const float2*>(in_octaves_host[o]));
   }
   a.win = win; a.scale = nullptr; a.BS = w.bufS; a.planar = planar ? 1 : 0;
   cudaFuncSetAttribute(k_cqt_synth_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_cqt_synth_bands<<<dim3(items, B), BAND_THREADS, smem, st>>>(a);
+  k_cqt_synth_bands<<<dim3(items, (B + a.rows_per_cta - 1) / a.rows_per_cta), BAND_THREADS, smem, st>>>(a);
   rc = check_launch("k_cqt_synth_bands");
   if (rc) return rc;
   GatherArgs g{};
