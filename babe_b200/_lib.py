@@ -5,7 +5,7 @@ caller gets an exception.  Build it with ``python -m babe_b200.build``.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbabe_b200.so")
@@ -67,6 +67,16 @@ SIGNATURES = {
                            c_void_p, c_int, c_void_p]),
     "babe_fir_filter": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p]),
+    "babe_gn_slices": (c_int, [c_int, c_int, c_int, c_longlong]),
+    "babe_gn_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_void_p]),
+    "babe_gn_film_gelu": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                  c_int, c_longlong, c_float, c_void_p]),
+    "babe_gate_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong,
+                                   c_float, c_void_p]),
+    "babe_gn_bwd_slices": (c_int, [c_int, c_int, c_longlong]),
+    "babe_gn_film_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                      c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_float,
+                                      c_float, c_void_p]),
     "babe_stft_stats_workspace": (c_size_t, [c_int, c_int, c_int]),
     "babe_stft_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

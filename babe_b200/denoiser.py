@@ -18,6 +18,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import net_ops
+
 
 def _init(shape, mode, fan_in, fan_out):
     """networks/cqtdiff+.py:21-26."""
@@ -30,6 +32,16 @@ def _init(shape, mode, fan_in, fan_out):
     if mode == 'kaiming_normal':
         return np.sqrt(1 / fan_in) * torch.randn(*shape)
     raise ValueError(f'Invalid init mode "{mode}"')
+
+
+FUSED = True          # use the fused CUDA glue (net_ops) when the parameters are frozen
+
+
+def _add_scale(a, b):
+    """(a + b) / sqrt(2)"""
+    if FUSED and a.shape == b.shape and net_ops.usable(a) and b.is_cuda and b.dtype == torch.float32:
+        return net_ops.add_scale(a, b)
+    return (a + b) / (2 ** 0.5)
 
 
 class Linear(nn.Module):
@@ -123,12 +135,17 @@ class ResnetBlock(nn.Module):
     def forward(self, input_x, sigma):
         x = self.proj_in(input_x)
         for norm, affine, gate, conv in zip(self.norm, self.affine, self.gate, self.H):
+            if FUSED and net_ops.usable(x, norm.gamma, conv.weight, affine.weight, gate.weight, sigma):
+                # csrc/net_ops.cu: 3 launches around the convolution instead of ~8 PyTorch kernels
+                x = net_ops.res_layer(x, norm.gamma, affine(sigma), gate(sigma), conv.weight,
+                                      conv.dilation, norm.num_groups, norm.eps)
+                continue
             x0 = x
             x = norm(x) * (affine(sigma)[:, :, None, None] + 1)
             x = (x0 + conv(F.gelu(x)) * gate(sigma)[:, :, None, None]) / (2 ** 0.5)
         if self.proj_place == 'after':
             x = self.proj_out(x)
-        return (x + self.res_conv(input_x)) / (2 ** 0.5)
+        return _add_scale(x, self.res_conv(input_x))
 
 
 _CUBIC = [-0.01171875, -0.03515625, 0.11328125, 0.43359375,
@@ -245,14 +262,14 @@ class CQTDiffPlus(nn.Module):
             hs.append(X)
             if i < last:
                 X = self.downsamplerT(X)
-            X = (X + pyr_proj(pyr)) / (2 ** 0.5)
+            X = _add_scale(X, pyr_proj(pyr))
         for out_block, res_block in self.middle:
             X = res_block(X, emb)
             Xout = out_block(X, emb)
         for i, (out_block, res_block) in enumerate(self.ups):
             j = len(self.ups) - i - 1
             X = res_block(torch.cat((X, hs.pop()), dim=1), emb)
-            Xout = (Xout + out_block(X, emb)) / (2 ** 0.5)
+            Xout = _add_scale(Xout, out_block(X, emb))
             X = X[:, :, self.bins_per_oct:, :]
             Out, Xout = Xout[:, :, :self.bins_per_oct, :], Xout[:, :, self.bins_per_oct:, :]
             if planar:

@@ -1,0 +1,147 @@
+"""Fused element-wise glue of the CQTDiff+ residual layers (csrc/net_ops.cu) behind
+``torch.autograd.Function`` boundaries.
+
+One dilated-convolution layer of ``ResnetBlock.forward`` (networks/cqtdiff+.py:470-482)
+
+    x -> (x + conv(gelu(norm(x) * (affine(sigma) + 1))) * gate(sigma)) / sqrt(2)
+
+is ~8 PyTorch kernels forward and ~16 backward around the convolution, most of them
+non-vectorised broadcast multiplies (45 % of the sampler step in the round-1 launch
+list).  Here it is 3 launches forward and 3 backward around the cuDNN convolution;
+only the layer input is saved for the backward pass.  Gradients are produced for the
+activations only: the functions are used when the parameters are frozen (sampling);
+``denoiser.py`` falls back to the composite PyTorch expression otherwise.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import profiling
+from ._lib import check, lib
+
+RSQRT2 = 0.7071067811865476
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gn_stats(x, groups):
+    N, C, Fd, T = x.shape
+    P = Fd * T
+    S = lib().babe_gn_slices(N, C, groups, P)
+    part = torch.empty(N * groups * S * 2, dtype=torch.float64, device=x.device)
+    with profiling.op("gn_stats", 1, 4 * x.numel()):
+        check(lib().babe_gn_stats(_p(x), _p(part), N, C, groups, P, S, _stream()), "gn_stats")
+    return part, S
+
+
+def gn_film_gelu(x, part, S, gamma, aff, groups, eps):
+    N, C, Fd, T = x.shape
+    h = torch.empty_like(x)
+    with profiling.op("gn_film_gelu", 1, 8 * x.numel()):
+        check(lib().babe_gn_film_gelu(_p(x), _p(h), _p(part), S, _p(gamma), _p(aff), N, C, groups,
+                                      Fd * T, eps, _stream()), "gn_film_gelu")
+    return h
+
+
+def gate_residual(x0, v, gate, scale=RSQRT2):
+    """(x0 + v * gate[n,c]) * scale; ``x0`` and ``gate`` may be None."""
+    N, C, Fd, T = v.shape
+    out = torch.empty_like(v)
+    with profiling.op("gate_residual", 1, (8 if x0 is None else 12) * v.numel()):
+        check(lib().babe_gate_residual(_p(x0), _p(v), _p(gate), _p(out), N, C, Fd * T, scale, _stream()),
+              "gate_residual")
+    return out
+
+
+def gn_film_gelu_bwd(gh, x, gy, part, S, gamma, aff, groups, eps, res_scale=RSQRT2):
+    N, C, Fd, T = x.shape
+    P = Fd * T
+    S2 = lib().babe_gn_bwd_slices(N, C, P)
+    scratch = torch.empty(N * C * S2, dtype=torch.float64, device=x.device)
+    gx = torch.empty_like(x)
+    with profiling.op("gn_film_gelu_bwd", 2, (24 if gy is not None else 20) * x.numel()):
+        check(lib().babe_gn_film_gelu_bwd(_p(gh), _p(x), _p(gy), _p(gx), _p(part), S, _p(scratch), S2,
+                                          _p(gamma), _p(aff), N, C, groups, P, eps, res_scale, _stream()),
+              "gn_film_gelu_bwd")
+    return gx
+
+
+def _same_padding(weight, dilation):
+    kh, kw = weight.shape[-2:]
+    if kh % 2 == 0 or kw % 2 == 0:
+        raise ValueError("fused residual layer needs odd kernel sizes")
+    return (dilation[0] * (kh - 1) // 2, dilation[1] * (kw - 1) // 2)
+
+
+def _rows(t, N, C):
+    t = t.detach().reshape(-1, C)
+    if t.shape[0] != N:
+        t = t.expand(N, C)
+    return t.contiguous().float()
+
+
+class _ResLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, aff, gate, weight, dilation, groups, eps):
+        x = x.contiguous()
+        N, C = x.shape[:2]
+        gamma = gamma.detach().reshape(-1).contiguous().float()
+        aff, gate = _rows(aff, N, C), _rows(gate, N, C)
+        weight = weight.detach()
+        pad = _same_padding(weight, dilation)
+        part, S = gn_stats(x, groups)
+        h = gn_film_gelu(x, part, S, gamma, aff, groups, eps)
+        v = F.conv2d(h, weight, None, 1, pad, dilation)
+        del h
+        y = gate_residual(x, v, gate)
+        ctx.save_for_backward(x, part, gamma, aff, gate, weight)
+        ctx.cfg = (S, dilation, groups, eps, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, part, gamma, aff, gate, weight = ctx.saved_tensors
+        S, dilation, groups, eps, pad = ctx.cfg
+        gy = gy.contiguous()
+        gv = gate_residual(None, gy, gate)
+        gh = torch.nn.grad.conv2d_input(x.shape, weight, gv, 1, pad, dilation)
+        del gv
+        gx = gn_film_gelu_bwd(gh.contiguous(), x, gy, part, S, gamma, aff, groups, eps)
+        return gx, None, None, None, None, None, None, None
+
+
+class _AddScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return gate_residual(a.contiguous(), b.contiguous(), None)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = gate_residual(None, g.contiguous(), None)
+        return g, g
+
+
+def _frozen(*ts):
+    return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts))
+
+
+def usable(x, *params):
+    """The fused path applies to CUDA float32 activations with frozen parameters."""
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and _frozen(*params)
+
+
+def res_layer(x, gamma, aff, gate, weight, dilation, groups, eps):
+    """(x + conv(gelu(groupnorm(x) * gamma * (aff + 1))) * gate) / sqrt(2), conv with "same" padding."""
+    return _ResLayer.apply(x, gamma, aff, gate, weight, tuple(dilation), groups, eps)
+
+
+def add_scale(a, b):
+    """(a + b) / sqrt(2)"""
+    return _AddScale.apply(a, b)

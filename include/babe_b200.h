@@ -216,6 +216,31 @@ int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const* in_octaves
                        float* x, int B, const float* win, const float* bin_scale, void* workspace,
                        size_t workspace_bytes, void* stream);   /* planar: networks/cqtdiff+.py:826-830 */
 
+/* ---- denoiser residual-layer glue (the caller either side of the CQT) ---- */
+/* One layer of ResnetBlock.forward (networks/cqtdiff+.py:470-482) around its convolution, on
+ * contiguous NCHW float32 activations x[N,C,F,T] (P = F*T):
+ *   h = gelu(BiasFreeGroupNorm_G(x) * gamma[c] * (aff[n,c] + 1))     (norm: networks/cqtdiff+.py:137-163,
+ *                                                                     x / (unbiased std of (n, group) + eps))
+ *   y = (x0 + v * gate[n,c]) * scale                                 (v = conv(h), scale = 1/sqrt(2))
+ * babe_gn_stats writes per-slice (sum, sum of squares) doubles part[N*G][slices][2]
+ * (slices = babe_gn_slices(...)); the consumers finish the statistics themselves. */
+int babe_gn_slices(int N, int C, int G, long long P);
+int babe_gn_stats(const float* x, double* part, int N, int C, int G, long long P, int slices,
+                  void* stream);
+int babe_gn_film_gelu(const float* x, float* h, const double* part, int slices, const float* gamma,
+                      const float* aff, int N, int C, int G, long long P, float eps, void* stream);
+/* gate == NULL: gate = 1;  x0 == NULL: out = v * gate * scale (the backward wrt v). */
+int babe_gate_residual(const float* x0, const float* v, const float* gate, float* out, int N, int C,
+                       long long P, float scale, void* stream);
+/* Backward of (babe_gn_stats + babe_gn_film_gelu) wrt x, with the residual branch folded in:
+ *   gx = gy * res_scale + d/dx <gh, h(x)>      (gy may be NULL)
+ * gr_part: scratch doubles [N*C][slices2], slices2 = babe_gn_bwd_slices(...). */
+int babe_gn_bwd_slices(int N, int C, long long P);
+int babe_gn_film_gelu_bwd(const float* gh, const float* x, const float* gy, float* gx,
+                          const double* part, int slices, double* gr_part, int slices2,
+                          const float* gamma, const float* aff, int N, int C, int G, long long P,
+                          float eps, float res_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,87 @@
+"""GPU: the fused residual-layer glue (csrc/net_ops.cu) against the composite PyTorch
+expression of networks/cqtdiff+.py:470-482 (fp32 reference of the same op), forward and
+gradient wrt the activations."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _composite(x, gamma, aff, gate, weight, dilation, groups, eps):
+    n, c, f, t = x.shape
+    xg = x.reshape(n, groups, -1)
+    xg = xg / (xg.std(-1, keepdim=True) + eps)
+    h = xg.reshape(n, c, f, t) * gamma
+    h = h * (aff[:, :, None, None] + 1)
+    v = F.conv2d(F.gelu(h), weight, padding="same", dilation=dilation)
+    return (x + v * gate[:, :, None, None]) / (2 ** 0.5)
+
+
+@pytest.mark.parametrize("shape,dil", [((2, 64, 64, 16), (1, 1)), ((3, 96, 20, 37), (4, 1)),
+                                       ((1, 256, 8, 130), (2, 1)), ((2, 16, 33, 1025), (1, 1))])
+def test_res_layer_matches_composite(shape, dil):
+    from babe_b200 import build, net_ops
+    build.build()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n, c = shape[:2]
+    x = (torch.randn(shape, device="cuda", generator=g) * 1.7 + 0.3).requires_grad_(True)
+    gamma = 1 + 0.2 * torch.randn(1, c, 1, 1, device="cuda", generator=g)
+    aff = 0.5 * torch.randn(n, c, device="cuda", generator=g)
+    gate = torch.randn(n, c, device="cuda", generator=g)
+    w = torch.randn(c, c, 5, 3, device="cuda", generator=g) / (c * 15) ** 0.5
+    gy = torch.randn(shape, device="cuda", generator=g)
+    y_ref = _composite(x, gamma, aff, gate, w, dil, 8, 1e-7)
+    gx_ref, = torch.autograd.grad(y_ref, x, gy)
+    y = net_ops.res_layer(x, gamma, aff, gate, w, dil, 8, 1e-7)
+    gx, = torch.autograd.grad(y, x, gy)
+    assert rel_l2(y, y_ref) < 1e-5
+    assert rel_l2(gx, gx_ref) < 1e-5
+    # bitwise reproducible
+    y2 = net_ops.res_layer(x, gamma, aff, gate, w, dil, 8, 1e-7)
+    assert torch.equal(y, y2)
+
+
+def test_add_scale():
+    from babe_b200 import build, net_ops
+    build.build()
+    a = torch.randn(2, 5, 7, 13, device="cuda", requires_grad=True)
+    b = torch.randn(2, 5, 7, 13, device="cuda", requires_grad=True)
+    y = net_ops.add_scale(a, b)
+    ga, gb = torch.autograd.grad(y, (a, b), torch.ones_like(y))
+    assert rel_l2(y, (a + b) / 2 ** 0.5) < 1e-6
+    assert rel_l2(ga, torch.full_like(a, 2 ** -0.5)) < 1e-6 and torch.equal(ga, gb)
+
+
+def test_denoiser_fused_matches_composite():
+    """Whole CQTDiff+ body (small configuration): fused glue vs composite PyTorch, frozen parameters."""
+    from babe_b200 import build, denoiser, sampler
+    build.build()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    args = sampler.make_args(sample_rate=22050, audio_len=16384)
+    args.network.Ns = [16, 16, 24, 24, 32, 32, 32]
+    args.network.num_dils = [1, 2, 2, 2, 2, 2, 2]
+    torch.manual_seed(0)
+    net = denoiser.CQTDiffPlus(args, "cuda").cuda()
+    # the gates are initialised ~0 (init_zero); give them weight so every branch matters
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if ".gate." in name:
+                p.mul_(3e6)
+    net.requires_grad_(False)
+    x = (torch.randn(2, 16384, device="cuda") * 0.1).requires_grad_(True)
+    sigma = torch.tensor([[0.5], [2.0]], device="cuda")
+    outs = []
+    for fused in (False, True):
+        denoiser.FUSED = fused
+        y = net(x, sigma)
+        gx, = torch.autograd.grad(y.square().sum(), x)
+        outs.append((y.detach(), gx))
+    denoiser.FUSED = True
+    assert rel_l2(outs[1][0], outs[0][0]) < 2e-5
+    assert rel_l2(outs[1][1], outs[0][1]) < 1e-4
