@@ -77,6 +77,7 @@ SIGNATURES = {
     "babe_gn_film_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_float,
                                       c_float, c_void_p]),
+    "babe_resample2": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_int, c_void_p]),
     "babe_stft_stats_workspace": (c_size_t, [c_int, c_int, c_int]),
     "babe_stft_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -300,6 +300,134 @@ __global__ void __launch_bounds__(NET_THREADS) k_gn_bwd(const float* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// x2 anti-aliased time resampling of UpDownResample (networks/cqtdiff+.py:522-580, mode "T"):
+// every (n, c, f) row is filtered independently by the L-tap kernel (the reference builds a dense
+// diagonal C x C x L weight per call, :564-570), reflect padding fused, and the two adjoints.
+//   down : xp = reflect_pad(x, pad),            y[t] = sum_k w[k] xp[2 t + k]          (T -> T/2)
+//   up   : xp = reflect_pad(x, (pad + 1) / 2),  y[j] = sum_k w[k] xp[(j + 2 pad + 1 - k) / 2]
+//          over the k of matching parity                                              (T -> 2 T)
+// with pad = L/2 - 1.  All four kernels are gathers (deterministic).
+// ---------------------------------------------------------------------------
+template <int L>
+struct Taps { float w[L]; };
+
+__device__ __forceinline__ int reflect_idx(int i, int T) {
+  if (i < 0) i = -i;
+  if (i >= T) i = 2 * (T - 1) - i;
+  return i;
+}
+
+template <int L>
+__global__ void __launch_bounds__(NET_THREADS) k_resample_down(const float* __restrict__ x,
+                                                               float* __restrict__ y, int T, int To,
+                                                               const Taps<L> w) {
+  constexpr int PAD = L / 2 - 1;
+  const int t = blockIdx.x * NET_THREADS + threadIdx.x;
+  if (t >= To) return;
+  const float* xr = x + (size_t)blockIdx.y * T;
+  float acc = 0.f;
+  const int q0 = 2 * t - PAD;
+  if (q0 >= 0 && q0 + L <= T) {
+#pragma unroll
+    for (int k = 0; k < L; ++k) acc = fmaf(w.w[k], xr[q0 + k], acc);
+  } else {
+#pragma unroll
+    for (int k = 0; k < L; ++k) acc = fmaf(w.w[k], xr[reflect_idx(q0 + k, T)], acc);
+  }
+  y[(size_t)blockIdx.y * To + t] = acc;
+}
+
+template <int L>
+__global__ void __launch_bounds__(NET_THREADS) k_resample_up(const float* __restrict__ x,
+                                                             float* __restrict__ y, int T,
+                                                             const Taps<L> w) {
+  constexpr int PAD = L / 2 - 1, PU = (PAD + 1) / 2;
+  const int j = blockIdx.x * NET_THREADS + threadIdx.x;
+  if (j >= 2 * T) return;
+  const float* xr = x + (size_t)blockIdx.y * T;
+  float acc = 0.f;
+  const int par = (j + 2 * PAD + 1) & 1;
+#pragma unroll
+  for (int kk = 0; kk < L / 2; ++kk) {
+    // k = par + 2 kk (same parity as j + 2 pad + 1); L/2 taps per output
+    const int i = (j + 2 * PAD + 1 - par) / 2 - kk;             // index into the padded row
+    const float wk = par ? w.w[2 * kk + 1] : w.w[2 * kk];
+    acc = fmaf(wk, xr[reflect_idx(i - PU, T)], acc);
+  }
+  y[(size_t)blockIdx.y * 2 * T + j] = acc;
+}
+
+// gradient of `down` wrt x: gy[To] -> gx[T]
+template <int L>
+__global__ void __launch_bounds__(NET_THREADS) k_resample_down_adj(const float* __restrict__ gy,
+                                                                   float* __restrict__ gx, int T, int To,
+                                                                   const Taps<L> w) {
+  constexpr int PAD = L / 2 - 1;
+  const int i = blockIdx.x * NET_THREADS + threadIdx.x;
+  if (i >= T) return;
+  const float* gr = gy + (size_t)blockIdx.y * To;
+  // padded-row gradient at q: sum over (t, k) with 2 t + k = q
+  auto gxp = [&](int q) {
+    float a = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < L / 2; ++kk) {
+      const int k = (q & 1) + 2 * kk, t = (q - k) / 2;
+      const float wk = (q & 1) ? w.w[2 * kk + 1] : w.w[2 * kk];
+      if (t >= 0 && t < To && q - k >= 0) a = fmaf(wk, gr[t], a);
+    }
+    return a;
+  };
+  float acc = gxp(i + PAD);
+  if (i >= 1 && i <= PAD) acc += gxp(PAD - i);                        // left reflection
+  if (i <= T - 2 && i >= T - 1 - PAD) acc += gxp(2 * (T - 1) - i + PAD);   // right reflection
+  gx[(size_t)blockIdx.y * T + i] = acc;
+}
+
+// gradient of `up` wrt x: gy[2T] -> gx[T]
+template <int L>
+__global__ void __launch_bounds__(NET_THREADS) k_resample_up_adj(const float* __restrict__ gy,
+                                                                 float* __restrict__ gx, int T,
+                                                                 const Taps<L> w) {
+  constexpr int PAD = L / 2 - 1, PU = (PAD + 1) / 2;
+  const int i = blockIdx.x * NET_THREADS + threadIdx.x;
+  if (i >= T) return;
+  const float* gr = gy + (size_t)blockIdx.y * 2 * T;
+  // padded-row gradient at q: sum_k w[k] gy[2 q + k - (2 pad + 1)]
+  auto gxp = [&](int q) {
+    float a = 0.f;
+    const int j0 = 2 * q - (2 * PAD + 1);
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      const int j = j0 + k;
+      if (j >= 0 && j < 2 * T) a = fmaf(w.w[k], gr[j], a);
+    }
+    return a;
+  };
+  float acc = gxp(i + PU);
+  if (i >= 1 && i <= PU) acc += gxp(PU - i);
+  if (i <= T - 2 && i >= T - 1 - PU) acc += gxp(2 * (T - 1) - i + PU);
+  gx[(size_t)blockIdx.y * T + i] = acc;
+}
+
+template <int L>
+static int launch_resample(const float* x, float* y, long long rows, int T, int mode, const float* taps,
+                           cudaStream_t st) {
+  Taps<L> w;
+  for (int k = 0; k < L; ++k) w.w[k] = taps[k];
+  const int To = T / 2;
+  const int n_out = mode == 0 ? To : (mode == 1 ? 2 * T : T);
+  const dim3 grid((n_out + NET_THREADS - 1) / NET_THREADS, (unsigned)rows);
+  switch (mode) {
+    case 0: k_resample_down<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, To, w); break;
+    case 1: k_resample_up<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, w); break;
+    case 2: k_resample_down_adj<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, To, w); break;
+    default: k_resample_up_adj<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, w); break;
+  }
+  return check_launch("k_resample");
+}
+
 static int check_dims(int N, int C, int G, long long P, const char* what) {
   BABE_REQUIRE(N >= 1 && C >= 1 && G >= 1 && P >= 1 && C % G == 0, BABE_EBADARG,
                "%s: bad shape N=%d C=%d G=%d P=%lld", what, N, C, G, P);
@@ -378,4 +506,29 @@ extern "C" int babe_gn_film_gelu_bwd(const float* gh, const float* x, const floa
   if (rc) return rc;
   k_gn_bwd<<<dim3(chunks_of(P), N * C), NET_THREADS, 0, st>>>(gh, x, gy, gx, a);
   return check_launch("k_gn_bwd");
+}
+
+extern "C" int babe_resample2(const float* in, float* out, long long rows, int T, int mode,
+                              const float* taps_host, int L, void* stream) {
+  BABE_REQUIRE(in && out && taps_host && rows >= 1, BABE_EBADARG, "resample2: bad arguments");
+  BABE_REQUIRE(mode >= 0 && mode <= 3, BABE_EBADARG, "resample2: mode %d", mode);
+  BABE_REQUIRE(T >= L && T % 2 == 0, BABE_EUNSUPPORTED, "resample2: row length %d (even, >= %d)", T, L);
+  BABE_REQUIRE(rows <= 65535LL * 32768, BABE_EUNSUPPORTED, "resample2: too many rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // grid.y is limited to 65535: split the rows
+  const long long step = 65535;
+  for (long long r0 = 0; r0 < rows; r0 += step) {
+    const long long nr = std::min(step, rows - r0);
+    const size_t in_len = (mode == 2) ? T / 2 : (mode == 3 ? 2 * (size_t)T : T);
+    const size_t out_len = (mode == 0) ? T / 2 : (mode == 1 ? 2 * (size_t)T : T);
+    int rc;
+    switch (L) {
+      case 4: rc = launch_resample<4>(in + r0 * in_len, out + r0 * out_len, nr, T, mode, taps_host, st); break;
+      case 8: rc = launch_resample<8>(in + r0 * in_len, out + r0 * out_len, nr, T, mode, taps_host, st); break;
+      case 12: rc = launch_resample<12>(in + r0 * in_len, out + r0 * out_len, nr, T, mode, taps_host, st); break;
+      default: BABE_REQUIRE(false, BABE_EUNSUPPORTED, "resample2: %d taps (4, 8 or 12)", L);
+    }
+    if (rc) return rc;
+  }
+  return BABE_OK;
 }

@@ -165,6 +165,9 @@ class UpDownResample(nn.Module):
 
     def forward(self, x):
         c = x.shape[1]
+        if FUSED and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] % 2 == 0 \
+                and x.shape[-1] >= len(_CUBIC):
+            return net_ops.resample2(x, _CUBIC, self.up)    # csrc/net_ops.cu: pad + FIR in one pass
         # depthwise (1 x 8) convolution along time: one FIR per (channel, frequency) row
         w = self.kernel.to(x.dtype)[None, None, None, :].expand(c, 1, 1, -1)
         if self.down:

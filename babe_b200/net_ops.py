@@ -145,3 +145,36 @@ def res_layer(x, gamma, aff, gate, weight, dilation, groups, eps):
 def add_scale(a, b):
     """(a + b) / sqrt(2)"""
     return _AddScale.apply(a, b)
+
+
+# ---------------------------------------------------------------------------
+# x2 anti-aliased time resampling (UpDownResample, networks/cqtdiff+.py:522-580)
+# ---------------------------------------------------------------------------
+def _resample(x, taps, mode):
+    """mode 0 down / 1 up / 2 gradient of down / 3 gradient of up, along the last axis."""
+    x = x.contiguous()
+    Tin = x.shape[-1]
+    T = {0: Tin, 1: Tin, 2: 2 * Tin, 3: Tin // 2}[mode]          # x-side row length
+    Tout = {0: T // 2, 1: 2 * T, 2: T, 3: T}[mode]
+    rows = x.numel() // Tin
+    out = torch.empty(*x.shape[:-1], Tout, dtype=x.dtype, device=x.device)
+    w = (ctypes.c_float * len(taps))(*taps)
+    with profiling.op("resample2", 1, 4 * (x.numel() + out.numel())):
+        check(lib().babe_resample2(_p(x), _p(out), rows, T, mode, w, len(taps), _stream()), "resample2")
+    return out
+
+
+class _Resample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, taps, up):
+        ctx.taps, ctx.up = taps, up
+        return _resample(x, taps, 1 if up else 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _resample(g, ctx.taps, 3 if ctx.up else 2), None, None
+
+
+def resample2(x, taps, up):
+    """UpDownResample.forward for mode "T": x[..., T] -> [..., 2T] (up) or [..., T/2] (down)."""
+    return _Resample.apply(x, tuple(float(t) for t in taps), bool(up))

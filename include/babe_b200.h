@@ -241,6 +241,14 @@ int babe_gn_film_gelu_bwd(const float* gh, const float* x, const float* gy, floa
                           const float* gamma, const float* aff, int N, int C, int G, long long P,
                           float eps, float res_scale, void* stream);
 
+/* x2 anti-aliased time resampling of UpDownResample (networks/cqtdiff+.py:522-580, mode "T",
+ * reflect padding fused) on `rows` independent rows; T = length of the x-side row (even):
+ *   mode 0: down   in[rows][T]   -> out[rows][T/2]     mode 2: gradient of mode 0, in[rows][T/2] -> out[rows][T]
+ *   mode 1: up     in[rows][T]   -> out[rows][2T]      mode 3: gradient of mode 1, in[rows][2T]  -> out[rows][T]
+ * taps_host: the L = 4, 8 or 12 filter taps (host memory; `_kernels`, networks/cqtdiff+.py:509-521). */
+int babe_resample2(const float* in, float* out, long long rows, int T, int mode,
+                   const float* taps_host, int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,35 @@ def test_add_scale():
     assert rel_l2(ga, torch.full_like(a, 2 ** -0.5)) < 1e-6 and torch.equal(ga, gb)
 
 
+@pytest.mark.parametrize("T", [8, 16, 50, 1024])
+@pytest.mark.parametrize("up", [False, True])
+def test_resample_matches_reference_formulation(T, up):
+    """networks/cqtdiff+.py:522-580 restated literally (dense diagonal weight, conv1d / conv_transpose1d)."""
+    from babe_b200 import build, denoiser, net_ops
+    build.build()
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(T)
+    x = torch.randn(2, 3, 5, T, device="cuda", generator=g, requires_grad=True)
+    k = torch.tensor(denoiser._CUBIC, device="cuda")
+    pad = len(denoiser._CUBIC) // 2 - 1
+    xr = x.view(-1, x.shape[-2], x.shape[-1])
+    w = xr.new_zeros(xr.shape[1], xr.shape[1], k.numel())
+    idx = torch.arange(xr.shape[1], device="cuda")
+    w[idx, idx] = k
+    if up:
+        ref = F.conv_transpose1d(F.pad(xr, ((pad + 1) // 2,) * 2, "reflect"), w, stride=2, padding=pad * 2 + 1)
+    else:
+        ref = F.conv1d(F.pad(xr, (pad,) * 2, "reflect"), w, stride=2)
+    ref = ref.view(2, 3, 5, -1)
+    y = net_ops.resample2(x, denoiser._CUBIC, up)
+    assert y.shape == ref.shape
+    assert rel_l2(y, ref) < 1e-6
+    gy = torch.randn(ref.shape, device="cuda", generator=g)
+    g_ref, = torch.autograd.grad(ref, x, gy)
+    g_new, = torch.autograd.grad(y, x, gy)
+    assert rel_l2(g_new, g_ref) < 1e-6
+
+
 def test_denoiser_fused_matches_composite():
     """Whole CQTDiff+ body (small configuration): fused glue vs composite PyTorch, frozen parameters."""
     from babe_b200 import build, denoiser, sampler
