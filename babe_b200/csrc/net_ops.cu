@@ -319,96 +319,206 @@ __device__ __forceinline__ int reflect_idx(int i, int T) {
   return i;
 }
 
+// Four outputs per thread; interior threads of the 8-tap filter use aligned vector loads:
+//   corr4  : out[m] = sum_k w[k] v[2 m + 1 + k],  v = in[2 o0 - 4 .. 2 o0 + 11]       (down, grad of up)
+//   interp4: out[m] from u = in[o0/2 - 2 .. o0/2 + 3], 4 taps of alternating parity   (up, grad of down)
+template <int L>
+__device__ __forceinline__ void corr4(const float* __restrict__ in, int o0, const Taps<L>& w, float (&o)[4]) {
+  float v[16];
+  const float4* p = reinterpret_cast<const float4*>(in + 2 * o0 - 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float4 q = p[i]; v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a = fmaf(w.w[k], v[2 * m + 1 + k], a);
+    o[m] = a;
+  }
+}
+template <int L>
+__device__ __forceinline__ void interp4(const float* __restrict__ in, int o0, const Taps<L>& w, float (&o)[4]) {
+  float u[6];
+  const float2* p = reinterpret_cast<const float2*>(in + o0 / 2 - 2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { const float2 q = p[i]; u[2 * i] = q.x; u[2 * i + 1] = q.y; }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    a0 = fmaf(w.w[2 * kk + 1], u[3 - kk], a0);
+    a1 = fmaf(w.w[2 * kk], u[4 - kk], a1);
+    a2 = fmaf(w.w[2 * kk + 1], u[4 - kk], a2);
+    a3 = fmaf(w.w[2 * kk], u[5 - kk], a3);
+  }
+  o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
+}
+__device__ __forceinline__ void store4(float* out, int o0, int n_out, const float (&o)[4], bool vec) {
+  if (vec && o0 + 3 < n_out) {
+    *reinterpret_cast<float4*>(out + o0) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      if (o0 + m < n_out) out[o0 + m] = o[m];
+  }
+}
+__device__ __forceinline__ bool aligned16(const void* a, const void* b) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
 template <int L>
 __global__ void __launch_bounds__(NET_THREADS) k_resample_down(const float* __restrict__ x,
                                                                float* __restrict__ y, int T, int To,
-                                                               const Taps<L> w) {
+                                                               const Taps<L> w, long long rows) {
   constexpr int PAD = L / 2 - 1;
-  const int t = blockIdx.x * NET_THREADS + threadIdx.x;
-  if (t >= To) return;
-  const float* xr = x + (size_t)blockIdx.y * T;
-  float acc = 0.f;
-  const int q0 = 2 * t - PAD;
-  if (q0 >= 0 && q0 + L <= T) {
-#pragma unroll
-    for (int k = 0; k < L; ++k) acc = fmaf(w.w[k], xr[q0 + k], acc);
+  const int per = (To + 3) / 4;                          // threads per row
+  const long long gidx = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
+  const long long row = gidx / per;
+  if (row >= rows) return;
+  const int t0 = 4 * (int)(gidx - row * per);
+  const float* xr = x + (size_t)row * T;
+  float* yr = y + (size_t)row * To;
+  const bool vec = aligned16(xr, yr);
+  float o[4];
+  if (L == 8 && vec && t0 >= 2 && 2 * t0 + 11 < T) {
+    corr4<L>(xr, t0, w, o);
   } else {
 #pragma unroll
-    for (int k = 0; k < L; ++k) acc = fmaf(w.w[k], xr[reflect_idx(q0 + k, T)], acc);
+    for (int m = 0; m < 4; ++m) {
+      float acc = 0.f;
+      const int q0 = 2 * (t0 + m) - PAD;
+      if (t0 + m < To) {
+#pragma unroll
+        for (int k = 0; k < L; ++k) acc = fmaf(w.w[k], xr[reflect_idx(q0 + k, T)], acc);
+      }
+      o[m] = acc;
+    }
   }
-  y[(size_t)blockIdx.y * To + t] = acc;
+  store4(yr, t0, To, o, vec);
 }
 
 template <int L>
 __global__ void __launch_bounds__(NET_THREADS) k_resample_up(const float* __restrict__ x,
                                                              float* __restrict__ y, int T,
-                                                             const Taps<L> w) {
+                                                             const Taps<L> w, long long rows) {
   constexpr int PAD = L / 2 - 1, PU = (PAD + 1) / 2;
-  const int j = blockIdx.x * NET_THREADS + threadIdx.x;
-  if (j >= 2 * T) return;
-  const float* xr = x + (size_t)blockIdx.y * T;
-  float acc = 0.f;
-  const int par = (j + 2 * PAD + 1) & 1;
+  const int per = (2 * T + 3) / 4;
+  const long long gidx = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
+  const long long row = gidx / per;
+  if (row >= rows) return;
+  const int j0 = 4 * (int)(gidx - row * per);
+  const float* xr = x + (size_t)row * T;
+  float* yr = y + (size_t)row * 2 * T;
+  const bool vec = aligned16(xr, yr);
+  float o[4];
+  if (L == 8 && vec && j0 >= 4 && j0 / 2 + 3 < T) {
+    interp4<L>(xr, j0, w, o);
+  } else {
 #pragma unroll
-  for (int kk = 0; kk < L / 2; ++kk) {
-    // k = par + 2 kk (same parity as j + 2 pad + 1); L/2 taps per output
-    const int i = (j + 2 * PAD + 1 - par) / 2 - kk;             // index into the padded row
-    const float wk = par ? w.w[2 * kk + 1] : w.w[2 * kk];
-    acc = fmaf(wk, xr[reflect_idx(i - PU, T)], acc);
+    for (int m = 0; m < 4; ++m) {
+      const int j = j0 + m;
+      float acc = 0.f;
+      const int par = (j + 2 * PAD + 1) & 1;
+      if (j < 2 * T) {
+#pragma unroll
+        for (int kk = 0; kk < L / 2; ++kk) {
+          // k = par + 2 kk (same parity as j + 2 pad + 1); L/2 taps per output
+          const int i = (j + 2 * PAD + 1 - par) / 2 - kk;             // index into the padded row
+          const float wk = par ? w.w[2 * kk + 1] : w.w[2 * kk];
+          acc = fmaf(wk, xr[reflect_idx(i - PU, T)], acc);
+        }
+      }
+      o[m] = acc;
+    }
   }
-  y[(size_t)blockIdx.y * 2 * T + j] = acc;
+  store4(yr, j0, 2 * T, o, vec);
 }
 
 // gradient of `down` wrt x: gy[To] -> gx[T]
 template <int L>
 __global__ void __launch_bounds__(NET_THREADS) k_resample_down_adj(const float* __restrict__ gy,
                                                                    float* __restrict__ gx, int T, int To,
-                                                                   const Taps<L> w) {
+                                                                   const Taps<L> w, long long rows) {
   constexpr int PAD = L / 2 - 1;
-  const int i = blockIdx.x * NET_THREADS + threadIdx.x;
-  if (i >= T) return;
-  const float* gr = gy + (size_t)blockIdx.y * To;
-  // padded-row gradient at q: sum over (t, k) with 2 t + k = q
-  auto gxp = [&](int q) {
-    float a = 0.f;
+  const int per = (T + 3) / 4;
+  const long long gidx = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
+  const long long row = gidx / per;
+  if (row >= rows) return;
+  const int i0 = 4 * (int)(gidx - row * per);
+  const float* gr = gy + (size_t)row * To;
+  float* xr = gx + (size_t)row * T;
+  const bool vec = aligned16(gr, xr);
+  float o[4];
+  if (L == 8 && vec && i0 >= 4 && i0 + 8 <= T) {
+    interp4<L>(gr, i0, w, o);
+  } else {
+    // padded-row gradient at q: sum over (t, k) with 2 t + k = q
+    auto gxp = [&](int q) {
+      float a = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < L / 2; ++kk) {
-      const int k = (q & 1) + 2 * kk, t = (q - k) / 2;
-      const float wk = (q & 1) ? w.w[2 * kk + 1] : w.w[2 * kk];
-      if (t >= 0 && t < To && q - k >= 0) a = fmaf(wk, gr[t], a);
+      for (int kk = 0; kk < L / 2; ++kk) {
+        const int k = (q & 1) + 2 * kk, t = (q - k) / 2;
+        const float wk = (q & 1) ? w.w[2 * kk + 1] : w.w[2 * kk];
+        if (t >= 0 && t < To && q - k >= 0) a = fmaf(wk, gr[t], a);
+      }
+      return a;
+    };
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int i = i0 + m;
+      float acc = 0.f;
+      if (i < T) {
+        acc = gxp(i + PAD);
+        if (i >= 1 && i <= PAD) acc += gxp(PAD - i);                        // left reflection
+        if (i <= T - 2 && i >= T - 1 - PAD) acc += gxp(2 * (T - 1) - i + PAD);   // right reflection
+      }
+      o[m] = acc;
     }
-    return a;
-  };
-  float acc = gxp(i + PAD);
-  if (i >= 1 && i <= PAD) acc += gxp(PAD - i);                        // left reflection
-  if (i <= T - 2 && i >= T - 1 - PAD) acc += gxp(2 * (T - 1) - i + PAD);   // right reflection
-  gx[(size_t)blockIdx.y * T + i] = acc;
+  }
+  store4(xr, i0, T, o, vec);
 }
 
 // gradient of `up` wrt x: gy[2T] -> gx[T]
 template <int L>
 __global__ void __launch_bounds__(NET_THREADS) k_resample_up_adj(const float* __restrict__ gy,
                                                                  float* __restrict__ gx, int T,
-                                                                 const Taps<L> w) {
+                                                                 const Taps<L> w, long long rows) {
   constexpr int PAD = L / 2 - 1, PU = (PAD + 1) / 2;
-  const int i = blockIdx.x * NET_THREADS + threadIdx.x;
-  if (i >= T) return;
-  const float* gr = gy + (size_t)blockIdx.y * 2 * T;
-  // padded-row gradient at q: sum_k w[k] gy[2 q + k - (2 pad + 1)]
-  auto gxp = [&](int q) {
-    float a = 0.f;
-    const int j0 = 2 * q - (2 * PAD + 1);
+  const int per = (T + 3) / 4;
+  const long long gidx = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
+  const long long row = gidx / per;
+  if (row >= rows) return;
+  const int i0 = 4 * (int)(gidx - row * per);
+  const float* gr = gy + (size_t)row * 2 * T;
+  float* xr = gx + (size_t)row * T;
+  const bool vec = aligned16(gr, xr);
+  float o[4];
+  if (L == 8 && vec && i0 >= 4 && i0 + 8 <= T) {
+    corr4<L>(gr, i0, w, o);
+  } else {
+    // padded-row gradient at q: sum_k w[k] gy[2 q + k - (2 pad + 1)]
+    auto gxp = [&](int q) {
+      float a = 0.f;
+      const int j0 = 2 * q - (2 * PAD + 1);
 #pragma unroll
-    for (int k = 0; k < L; ++k) {
-      const int j = j0 + k;
-      if (j >= 0 && j < 2 * T) a = fmaf(w.w[k], gr[j], a);
+      for (int k = 0; k < L; ++k) {
+        const int j = j0 + k;
+        if (j >= 0 && j < 2 * T) a = fmaf(w.w[k], gr[j], a);
+      }
+      return a;
+    };
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int i = i0 + m;
+      float acc = 0.f;
+      if (i < T) {
+        acc = gxp(i + PU);
+        if (i >= 1 && i <= PU) acc += gxp(PU - i);
+        if (i <= T - 2 && i >= T - 1 - PU) acc += gxp(2 * (T - 1) - i + PU);
+      }
+      o[m] = acc;
     }
-    return a;
-  };
-  float acc = gxp(i + PU);
-  if (i >= 1 && i <= PU) acc += gxp(PU - i);
-  if (i <= T - 2 && i >= T - 1 - PU) acc += gxp(2 * (T - 1) - i + PU);
-  gx[(size_t)blockIdx.y * T + i] = acc;
+  }
+  store4(xr, i0, T, o, vec);
 }
 
 template <int L>
@@ -418,12 +528,13 @@ static int launch_resample(const float* x, float* y, long long rows, int T, int 
   for (int k = 0; k < L; ++k) w.w[k] = taps[k];
   const int To = T / 2;
   const int n_out = mode == 0 ? To : (mode == 1 ? 2 * T : T);
-  const dim3 grid((n_out + NET_THREADS - 1) / NET_THREADS, (unsigned)rows);
+  const long long threads = rows * ((n_out + 3) / 4);
+  const unsigned grid = (unsigned)((threads + NET_THREADS - 1) / NET_THREADS);
   switch (mode) {
-    case 0: k_resample_down<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, To, w); break;
-    case 1: k_resample_up<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, w); break;
-    case 2: k_resample_down_adj<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, To, w); break;
-    default: k_resample_up_adj<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, w); break;
+    case 0: k_resample_down<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, To, w, rows); break;
+    case 1: k_resample_up<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, w, rows); break;
+    case 2: k_resample_down_adj<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, To, w, rows); break;
+    default: k_resample_up_adj<L><<<grid, NET_THREADS, 0, st>>>(x, y, T, w, rows); break;
   }
   return check_launch("k_resample");
 }
@@ -513,22 +624,14 @@ extern "C" int babe_resample2(const float* in, float* out, long long rows, int T
   BABE_REQUIRE(in && out && taps_host && rows >= 1, BABE_EBADARG, "resample2: bad arguments");
   BABE_REQUIRE(mode >= 0 && mode <= 3, BABE_EBADARG, "resample2: mode %d", mode);
   BABE_REQUIRE(T >= L && T % 2 == 0, BABE_EUNSUPPORTED, "resample2: row length %d (even, >= %d)", T, L);
-  BABE_REQUIRE(rows <= 65535LL * 32768, BABE_EUNSUPPORTED, "resample2: too many rows");
+  BABE_REQUIRE(rows * (long long)T < (1LL << 40), BABE_EUNSUPPORTED, "resample2: too many rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // grid.y is limited to 65535: split the rows
-  const long long step = 65535;
-  for (long long r0 = 0; r0 < rows; r0 += step) {
-    const long long nr = std::min(step, rows - r0);
-    const size_t in_len = (mode == 2) ? T / 2 : (mode == 3 ? 2 * (size_t)T : T);
-    const size_t out_len = (mode == 0) ? T / 2 : (mode == 1 ? 2 * (size_t)T : T);
-    int rc;
-    switch (L) {
-      case 4: rc = launch_resample<4>(in + r0 * in_len, out + r0 * out_len, nr, T, mode, taps_host, st); break;
-      case 8: rc = launch_resample<8>(in + r0 * in_len, out + r0 * out_len, nr, T, mode, taps_host, st); break;
-      case 12: rc = launch_resample<12>(in + r0 * in_len, out + r0 * out_len, nr, T, mode, taps_host, st); break;
-      default: BABE_REQUIRE(false, BABE_EUNSUPPORTED, "resample2: %d taps (4, 8 or 12)", L);
-    }
-    if (rc) return rc;
+  int rc;
+  switch (L) {
+    case 4: rc = launch_resample<4>(in, out, rows, T, mode, taps_host, st); break;
+    case 8: rc = launch_resample<8>(in, out, rows, T, mode, taps_host, st); break;
+    case 12: rc = launch_resample<12>(in, out, rows, T, mode, taps_host, st); break;
+    default: BABE_REQUIRE(false, BABE_EUNSUPPORTED, "resample2: %d taps (4, 8 or 12)", L);
   }
-  return BABE_OK;
+  return rc;
 }
