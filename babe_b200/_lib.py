@@ -74,6 +74,8 @@ SIGNATURES = {
     "babe_gate_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong,
                                    c_float, c_void_p]),
     "babe_gn_bwd_slices": (c_int, [c_int, c_int, c_longlong]),
+    "babe_gn_film_gelu_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                             c_void_p, c_int, c_int, c_int, c_longlong, c_float, c_void_p]),
     "babe_gn_film_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_float,
                                       c_float, c_void_p]),

@@ -371,10 +371,10 @@ __global__ void __launch_bounds__(NET_THREADS) k_resample_down(const float* __re
                                                                const Taps<L> w, long long rows) {
   constexpr int PAD = L / 2 - 1;
   const int per = (To + 3) / 4;                          // threads per row
-  const long long gidx = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
-  const long long row = gidx / per;
+  const unsigned gidx = blockIdx.x * NET_THREADS + threadIdx.x;   // < 2^32 (checked by the launcher)
+  const unsigned row = gidx / (unsigned)per;
   if (row >= rows) return;
-  const int t0 = 4 * (int)(gidx - row * per);
+  const int t0 = 4 * (int)(gidx - row * (unsigned)per);
   const float* xr = x + (size_t)row * T;
   float* yr = y + (size_t)row * To;
   const bool vec = aligned16(xr, yr);
@@ -402,10 +402,10 @@ __global__ void __launch_bounds__(NET_THREADS) k_resample_up(const float* __rest
                                                              const Taps<L> w, long long rows) {
   constexpr int PAD = L / 2 - 1, PU = (PAD + 1) / 2;
   const int per = (2 * T + 3) / 4;
-  const long long gidx = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
-  const long long row = gidx / per;
+  const unsigned gidx = blockIdx.x * NET_THREADS + threadIdx.x;   // < 2^32 (checked by the launcher)
+  const unsigned row = gidx / (unsigned)per;
   if (row >= rows) return;
-  const int j0 = 4 * (int)(gidx - row * per);
+  const int j0 = 4 * (int)(gidx - row * (unsigned)per);
   const float* xr = x + (size_t)row * T;
   float* yr = y + (size_t)row * 2 * T;
   const bool vec = aligned16(xr, yr);
@@ -440,10 +440,10 @@ __global__ void __launch_bounds__(NET_THREADS) k_resample_down_adj(const float* 
                                                                    const Taps<L> w, long long rows) {
   constexpr int PAD = L / 2 - 1;
   const int per = (T + 3) / 4;
-  const long long gidx = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
-  const long long row = gidx / per;
+  const unsigned gidx = blockIdx.x * NET_THREADS + threadIdx.x;   // < 2^32 (checked by the launcher)
+  const unsigned row = gidx / (unsigned)per;
   if (row >= rows) return;
-  const int i0 = 4 * (int)(gidx - row * per);
+  const int i0 = 4 * (int)(gidx - row * (unsigned)per);
   const float* gr = gy + (size_t)row * To;
   float* xr = gx + (size_t)row * T;
   const bool vec = aligned16(gr, xr);
@@ -484,10 +484,10 @@ __global__ void __launch_bounds__(NET_THREADS) k_resample_up_adj(const float* __
                                                                  const Taps<L> w, long long rows) {
   constexpr int PAD = L / 2 - 1, PU = (PAD + 1) / 2;
   const int per = (T + 3) / 4;
-  const long long gidx = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
-  const long long row = gidx / per;
+  const unsigned gidx = blockIdx.x * NET_THREADS + threadIdx.x;   // < 2^32 (checked by the launcher)
+  const unsigned row = gidx / (unsigned)per;
   if (row >= rows) return;
-  const int i0 = 4 * (int)(gidx - row * per);
+  const int i0 = 4 * (int)(gidx - row * (unsigned)per);
   const float* gr = gy + (size_t)row * 2 * T;
   float* xr = gx + (size_t)row * T;
   const bool vec = aligned16(gr, xr);
@@ -555,7 +555,7 @@ using namespace babe;
 extern "C" int babe_gn_slices(int N, int C, int G, long long P) {
   if (N < 1 || C < 1 || G < 1 || P < 1 || C % G) return 0;
   const long long cnt = (long long)(C / G) * P;
-  long long s = (4LL * sm_count() + (long long)N * G - 1) / ((long long)N * G);
+  long long s = (16LL * sm_count() + (long long)N * G - 1) / ((long long)N * G);
   s = std::min<long long>(s, (cnt + 8191) / 8192);
   return (int)std::max<long long>(1, std::min<long long>(s, MAX_STAT_SLICES));
 }
@@ -595,13 +595,28 @@ extern "C" int babe_gate_residual(const float* x0, const float* v, const float* 
 
 extern "C" int babe_gn_bwd_slices(int N, int C, long long P) {
   if (N < 1 || C < 1 || P < 1) return 0;
-  long long s = (4LL * sm_count() + (long long)N * C - 1) / ((long long)N * C);
+  long long s = (16LL * sm_count() + (long long)N * C - 1) / ((long long)N * C);
   s = std::min<long long>(s, (P + 4095) / 4096);
   return (int)std::max<long long>(1, std::min<long long>(s, 16));
 }
 
+extern "C" int babe_gn_film_gelu_bwd_reduce(const float* gh, const float* x, const double* part,
+                                            int slices, double* gr_part, int slices2,
+                                            const float* gamma, const float* aff, int N, int C, int G,
+                                            long long P, float eps, void* stream) {
+  int rc = check_dims(N, C, G, P, "gn_film_gelu_bwd_reduce");
+  if (rc) return rc;
+  BABE_REQUIRE(gh && x && part && gr_part && gamma && aff && slices >= 1 && slices2 >= 1, BABE_EBADARG,
+               "gn_film_gelu_bwd_reduce: bad arguments");
+  PlaneArgs a{};
+  a.N = N; a.C = C; a.G = G; a.S = slices; a.P = P; a.eps = eps;
+  a.part = part; a.gamma = gamma; a.aff = aff; a.gr_part = gr_part; a.S2 = slices2;
+  k_gn_bwd_reduce<<<dim3(slices2, N * C), NET_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(gh, x, gr_part, a);
+  return check_launch("k_gn_bwd_reduce");
+}
+
 extern "C" int babe_gn_film_gelu_bwd(const float* gh, const float* x, const float* gy, float* gx,
-                                     const double* part, int slices, double* gr_part, int slices2,
+                                     const double* part, int slices, const double* gr_part, int slices2,
                                      const float* gamma, const float* aff, int N, int C, int G,
                                      long long P, float eps, float res_scale, void* stream) {
   int rc = check_dims(N, C, G, P, "gn_film_gelu_bwd");
@@ -611,11 +626,7 @@ extern "C" int babe_gn_film_gelu_bwd(const float* gh, const float* x, const floa
   PlaneArgs a{};
   a.N = N; a.C = C; a.G = G; a.S = slices; a.P = P; a.eps = eps; a.scale = res_scale;
   a.part = part; a.gamma = gamma; a.aff = aff; a.gr_part = gr_part; a.S2 = slices2;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  k_gn_bwd_reduce<<<dim3(slices2, N * C), NET_THREADS, 0, st>>>(gh, x, gr_part, a);
-  rc = check_launch("k_gn_bwd_reduce");
-  if (rc) return rc;
-  k_gn_bwd<<<dim3(chunks_of(P), N * C), NET_THREADS, 0, st>>>(gh, x, gy, gx, a);
+  k_gn_bwd<<<dim3(chunks_of(P), N * C), NET_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(gh, x, gy, gx, a);
   return check_launch("k_gn_bwd");
 }
 
@@ -624,7 +635,7 @@ extern "C" int babe_resample2(const float* in, float* out, long long rows, int T
   BABE_REQUIRE(in && out && taps_host && rows >= 1, BABE_EBADARG, "resample2: bad arguments");
   BABE_REQUIRE(mode >= 0 && mode <= 3, BABE_EBADARG, "resample2: mode %d", mode);
   BABE_REQUIRE(T >= L && T % 2 == 0, BABE_EUNSUPPORTED, "resample2: row length %d (even, >= %d)", T, L);
-  BABE_REQUIRE(rows * (long long)T < (1LL << 40), BABE_EUNSUPPORTED, "resample2: too many rows");
+  BABE_REQUIRE(rows * (long long)T < (1LL << 31), BABE_EUNSUPPORTED, "resample2: more than 2^31 samples");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   switch (L) {

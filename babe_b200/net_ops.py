@@ -66,7 +66,10 @@ def gn_film_gelu_bwd(gh, x, gy, part, S, gamma, aff, groups, eps, res_scale=RSQR
     S2 = lib().babe_gn_bwd_slices(N, C, P)
     scratch = torch.empty(N * C * S2, dtype=torch.float64, device=x.device)
     gx = torch.empty_like(x)
-    with profiling.op("gn_film_gelu_bwd", 2, (24 if gy is not None else 20) * x.numel()):
+    with profiling.op("gn_bwd_reduce", 1, 8 * x.numel()):
+        check(lib().babe_gn_film_gelu_bwd_reduce(_p(gh), _p(x), _p(part), S, _p(scratch), S2, _p(gamma),
+                                                 _p(aff), N, C, groups, P, eps, _stream()), "gn_bwd_reduce")
+    with profiling.op("gn_film_gelu_bwd", 1, (16 if gy is not None else 12) * x.numel()):
         check(lib().babe_gn_film_gelu_bwd(_p(gh), _p(x), _p(gy), _p(gx), _p(part), S, _p(scratch), S2,
                                           _p(gamma), _p(aff), N, C, groups, P, eps, res_scale, _stream()),
               "gn_film_gelu_bwd")

@@ -234,10 +234,14 @@ int babe_gate_residual(const float* x0, const float* v, const float* gate, float
                        long long P, float scale, void* stream);
 /* Backward of (babe_gn_stats + babe_gn_film_gelu) wrt x, with the residual branch folded in:
  *   gx = gy * res_scale + d/dx <gh, h(x)>      (gy may be NULL)
- * gr_part: scratch doubles [N*C][slices2], slices2 = babe_gn_bwd_slices(...). */
+ * in two launches: _reduce fills gr_part[N*C][slices2] (slices2 = babe_gn_bwd_slices(...)) with the
+ * partial sums of the statistic's gradient, then babe_gn_film_gelu_bwd writes gx. */
 int babe_gn_bwd_slices(int N, int C, long long P);
+int babe_gn_film_gelu_bwd_reduce(const float* gh, const float* x, const double* part, int slices,
+                                 double* gr_part, int slices2, const float* gamma, const float* aff,
+                                 int N, int C, int G, long long P, float eps, void* stream);
 int babe_gn_film_gelu_bwd(const float* gh, const float* x, const float* gy, float* gx,
-                          const double* part, int slices, double* gr_part, int slices2,
+                          const double* part, int slices, const double* gr_part, int slices2,
                           const float* gamma, const float* aff, int N, int C, int G, long long P,
                           float eps, float res_scale, void* stream);
 
