@@ -182,6 +182,7 @@ def run_ours(a):
             if i == W + K - 1:
                 ev["e"] = torch.cuda.Event(enable_timing=True)
                 ev["e"].record()
+                ev["host"] = time.perf_counter() - ev["t0"]     # host time to enqueue the K steps
                 torch.cuda.synchronize()
                 ev["wall"] = time.perf_counter() - ev["t0"]
                 ev["launches"] = profiling.launches()
@@ -253,7 +254,8 @@ def run_ours(a):
                    "sample_rate": SR, "nfft": NFFT, "sampler_steps_per_s": round(K / (dev_run["ms"] / 1e3), 4),
                    "parallelism": f"replicas x{world} (independent chains, no data-path collective)",
                    "l2_note": "per-step working set (activations of the 44.5M-param U-Net at B=8, >10 GB) far exceeds the 126 MB L2",
-                   "tf32": bool(torch.backends.cudnn.allow_tf32)},
+                   "tf32": bool(torch.backends.cudnn.allow_tf32),
+                   "host_enqueue_ms_per_step": round(dev_run.get("host", 0.0) * 1e3 / K, 1)},
         "e2e": {"value": round(e2e_value, 4), "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_run["ms"] / K, 3)},
         "gpu_launches": dev_run["launches"],
