@@ -41,9 +41,16 @@ def test_res_layer_matches_composite(shape, dil):
     gx, = torch.autograd.grad(y, x, gy)
     assert rel_l2(y, y_ref) < 1e-5
     assert rel_l2(gx, gx_ref) < 1e-5
-    # bitwise reproducible
-    y2 = net_ops.res_layer(x, gamma, aff, gate, w, dil, 8, 1e-7)
-    assert torch.equal(y, y2)
+    # bitwise reproducible (the glue kernels always; cuDNN's dgrad kernels, which the convolution
+    # autotuner may pick for the forward pass, only in cuDNN's deterministic mode)
+    prev = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        y1 = net_ops.res_layer(x, gamma, aff, gate, w, dil, 8, 1e-7)
+        y2 = net_ops.res_layer(x, gamma, aff, gate, w, dil, 8, 1e-7)
+    finally:
+        torch.backends.cudnn.deterministic = prev
+    assert torch.equal(y1, y2)
 
 
 def test_add_scale():
