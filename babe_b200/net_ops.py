@@ -175,6 +175,33 @@ class _ResLayer(torch.autograd.Function):
         return gx, None, None, None, None, None, None, None
 
 
+class _ConvSame(torch.autograd.Function):
+    """Bias-free stride-1 "same" convolution with a frozen weight: both directions go through
+    ``conv_same`` (the faster of cuDNN's two formulations per shape)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, dilation):
+        weight = weight.detach()
+        pad = _same_padding(weight, dilation)
+        ctx.save_for_backward(weight)
+        ctx.cfg = (dilation, pad)
+        return conv_same(x.contiguous(), weight, pad, dilation)
+
+    @staticmethod
+    def backward(ctx, g):
+        weight, = ctx.saved_tensors
+        dilation, pad = ctx.cfg
+        return conv_same(g.contiguous(), weight, pad, dilation, transposed=True), None, None
+
+
+def _pair(d):
+    return (d, d) if isinstance(d, int) else tuple(d)
+
+
+def conv_frozen(x, weight, dilation):
+    return _ConvSame.apply(x, weight, _pair(dilation))
+
+
 class _AddScale(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
@@ -197,7 +224,7 @@ def usable(x, *params):
 
 def res_layer(x, gamma, aff, gate, weight, dilation, groups, eps):
     """(x + conv(gelu(groupnorm(x) * gamma * (aff + 1))) * gate) / sqrt(2), conv with "same" padding."""
-    return _ResLayer.apply(x, gamma, aff, gate, weight, tuple(dilation), groups, eps)
+    return _ResLayer.apply(x, gamma, aff, gate, weight, _pair(dilation), groups, eps)
 
 
 def add_scale(a, b):

@@ -181,9 +181,11 @@ def run_ours(a):
                 ev["t0"] = time.perf_counter()
                 ev["s"] = torch.cuda.Event(enable_timing=True)
                 ev["s"].record()
+                torch.cuda.nvtx.range_push("timed_" + mode)     # ncu --nvtx --nvtx-include "timed_device/"
             if i == W + K - 1:
                 ev["e"] = torch.cuda.Event(enable_timing=True)
                 ev["e"].record()
+                torch.cuda.nvtx.range_pop()
                 ev["host"] = time.perf_counter() - ev["t0"]     # host time to enqueue the K steps
                 torch.cuda.synchronize()
                 ev["wall"] = time.perf_counter() - ev["t0"]
