@@ -154,9 +154,13 @@ def rec_guidance_norms(x, y, freqs, filter_params, nfft):
 
 # ---------------------------------------------------------------------------
 class BlindSamplerFused:
-    def __init__(self, model, diff_params, args, rid=False, device_noise=False):
-        """testing/blind_bwe_sampler.py:14-47."""
+    def __init__(self, model, diff_params, args, rid=False, device_noise=False, freeze_model=True):
+        """testing/blind_bwe_sampler.py:14-47.  ``freeze_model``: sampling never needs parameter
+        gradients (the reference only takes ``autograd.grad(..., inputs=x)``, :120); freezing them lets
+        ``babe_b200.denoiser`` run its fused layer glue and skips the parameter-gradient branches."""
         self.model = model
+        if freeze_model and isinstance(model, torch.nn.Module):
+            model.requires_grad_(False)
         self.diff_params = diff_params
         self.args = args
         if not args.tester.diff_params.same_as_training:
