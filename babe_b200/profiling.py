@@ -31,6 +31,12 @@ def launches():
     return _launches
 
 
+def add_launches(n):
+    """Kernels replayed from a captured CUDA graph (the wrappers are not re-entered on replay)."""
+    global _launches
+    _launches += n
+
+
 @contextlib.contextmanager
 def op(name, kernels, nbytes):
     global _launches

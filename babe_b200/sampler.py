@@ -19,11 +19,13 @@ purely in execution:
   fixed ``torch.manual_seed``.
 """
 import types
+import warnings
 
 import torch
 
 from . import blind_bwe_utils as bu
 from . import ops
+from . import profiling
 from ._lib import FitConfig
 
 
@@ -154,13 +156,18 @@ def rec_guidance_norms(x, y, freqs, filter_params, nfft):
 
 # ---------------------------------------------------------------------------
 class BlindSamplerFused:
-    def __init__(self, model, diff_params, args, rid=False, device_noise=False, freeze_model=True):
+    def __init__(self, model, diff_params, args, rid=False, device_noise=False, freeze_model=True,
+                 cuda_graph=False):
         """testing/blind_bwe_sampler.py:14-47.  ``freeze_model``: sampling never needs parameter
         gradients (the reference only takes ``autograd.grad(..., inputs=x)``, :120); freezing them lets
         ``babe_b200.denoiser`` run its fused layer glue and skips the parameter-gradient branches."""
         self.model = model
         if freeze_model and isinstance(model, torch.nn.Module):
             model.requires_grad_(False)
+        # SURVEY 8f-1: replay the denoiser's forward and backward from two captured CUDA graphs (static
+        # shapes, frozen parameters, no host synchronisation inside the network)
+        self.cuda_graph = cuda_graph
+        self._graphed, self._graph_key, self._graph_launches = None, None, (0, 0)
         self.diff_params = diff_params
         self.args = args
         if not args.tester.diff_params.same_as_training:
@@ -201,10 +208,39 @@ class BlindSamplerFused:
     # -- pieces of one evaluation -------------------------------------------------
     def get_denoised_estimate(self, x, t_i):
         """testing/blind_bwe_sampler.py:152-157."""
-        x_hat = self.diff_params.denoiser(x, self.model, t_i.unsqueeze(-1))
+        net = self._graphed_model(x) if self.cuda_graph and x.is_cuda and x.requires_grad else self.model
+        x_hat = self.diff_params.denoiser(x, net, t_i.unsqueeze(-1))
         if self.args.tester.filter_out_cqt_DC_Nyq:
             x_hat = self.model.CQTransform.apply_hpf_DC(x_hat)
         return x_hat
+
+    def _graphed_model(self, x):
+        """The network as a callable replaying captured CUDA graphs (``torch.cuda.make_graphed_callables``:
+        one graph for the forward, one for the backward wrt the input); eager model on any failure."""
+        key = (tuple(x.shape), x.dtype, x.device)
+        if self._graph_key != key:
+            self._graph_key, self._graphed = key, None
+            try:
+                sx = torch.zeros_like(x).requires_grad_(True)
+                ss = torch.ones(1, 1, device=x.device, dtype=x.dtype)
+                l0 = profiling.launches()                  # launches of one eager forward / backward
+                out = self.model(sx, ss)
+                l1 = profiling.launches()
+                torch.autograd.grad(out.sum(), sx)
+                self._graph_launches = (l1 - l0, profiling.launches() - l1)
+                model = self.model
+                self._graphed = torch.cuda.make_graphed_callables(lambda a, b: model(a, b), (sx, ss))
+            except Exception as exc:                       # noqa: BLE001 - any capture problem: stay eager
+                warnings.warn(f"CUDA-graph capture of the denoiser failed ({exc!r}); running it eagerly")
+                self._graphed = None
+        if self._graphed is None:
+            return self.model
+        graphed, (lf, lb) = self._graphed, self._graph_launches
+
+        def net(a, sigma):
+            profiling.add_launches(lf + lb)               # replayed kernels of the forward + backward graphs
+            return graphed(a.contiguous(), sigma.reshape(1, 1).to(a.dtype))
+        return net
 
     def apply_filter_fcA(self, x, filter_params):
         """testing/blind_bwe_sampler.py:518-520, H designed inside the kernel."""

@@ -181,11 +181,13 @@ def run_ours(a):
                 ev["t0"] = time.perf_counter()
                 ev["s"] = torch.cuda.Event(enable_timing=True)
                 ev["s"].record()
-                torch.cuda.nvtx.range_push("timed_" + mode)     # ncu --nvtx --nvtx-include "timed_device/"
+                # process-wide start/end range (push/pop ranges are per thread and would miss the kernels
+                # launched by autograd's backward thread):  ncu --nvtx --nvtx-include "timed_device"
+                ev["nvtx"] = torch.cuda.nvtx.range_start("timed_" + mode)
             if i == W + K - 1:
                 ev["e"] = torch.cuda.Event(enable_timing=True)
                 ev["e"].record()
-                torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_end(ev["nvtx"])
                 ev["host"] = time.perf_counter() - ev["t0"]     # host time to enqueue the K steps
                 torch.cuda.synchronize()
                 ev["wall"] = time.perf_counter() - ev["t0"]
@@ -205,13 +207,18 @@ def run_ours(a):
 
     # `value`: device-resident run without per-call CUDA events; a second, identical pass with the
     # events on supplies the per-kernel table of `roofline` (the events cost host time only)
+    use_graph = not (a.no_cuda_graph or a.single_pass)      # ncu launch lists profile the eager launches
+    smp.cuda_graph = use_graph
     dev_run, _, _ = timed_run("device")
+    graphed = smp._graphed is not None
+    smp.cuda_graph = False               # the per-kernel pass needs the wrappers to run (eager)
     if a.single_pass:                    # ncu launch lists: exactly K timed steps, no second pass
         prof_run = dev_run
     else:
         profiling.enable(True)
         prof_run, _, _ = timed_run("device")
         profiling.enable(False)
+    smp.cuda_graph = use_graph
     if a.skip_e2e:                       # profiling runs (ncu) only need the device-resident leg
         e2e_run, h2d, d2h = dev_run, 0, 0
     else:
@@ -287,6 +294,7 @@ def run_ours(a):
                    "parallelism": f"replicas x{world} (independent chains, no data-path collective)",
                    "l2_note": "per-step working set (activations of the 44.5M-param U-Net at B=8, >10 GB) far exceeds the 126 MB L2",
                    "tf32": bool(torch.backends.cudnn.allow_tf32),
+                   "cuda_graph": graphed,
                    "host_enqueue_ms_per_step": round(dev_run.get("host", 0.0) * 1e3 / K, 1)},
         "e2e": {"value": round(e2e_value, 4), "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_run["ms"] / K, 3)},
@@ -547,6 +555,8 @@ def main():
     ap.add_argument("--shapes", default="")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="run the denoiser eagerly instead of replaying captured CUDA graphs")
     ap.add_argument("--single-pass", action="store_true",
                     help="profiling aid: skip the second (per-kernel event timing) pass")
     ap.add_argument("--no-autotune", action="store_true", help="profiling aid: cudnn.benchmark off")

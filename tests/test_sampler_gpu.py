@@ -70,6 +70,22 @@ def test_rid_outputs_and_device_noise(golden):
     assert torch.equal(x1, x2)
 
 
+def test_cuda_graph_replay_matches_eager(golden):
+    """the denoiser's forward/backward replayed from captured CUDA graphs."""
+    from babe_b200 import profiling
+    g, y, args, model, s = _setup(golden, max_iter=3)
+    torch.backends.cudnn.deterministic = True
+    torch.manual_seed(5)
+    x0, p0 = s.predict_blind_bwe(y.clone(), max_steps=3)
+    s.cuda_graph = True
+    torch.manual_seed(5)
+    n0 = profiling.launches()
+    x1, p1 = s.predict_blind_bwe(y.clone(), max_steps=3)
+    assert s._graphed is not None, "capture failed"
+    assert profiling.launches() > n0
+    assert rel_l2(x1, x0) < 1e-6 and rel_l2(p1, p0) < 1e-6
+
+
 def test_compute_sweep_matches_oracle(golden):
     """a14 (testing/blind_bwe_sampler.py:598-616): loss and (d/dfc, d/dA) on the 15x12 grid."""
     from oracle import filter_fit as ofit, stft_filter as osf
