@@ -221,13 +221,16 @@ class BlindSamplerFused:
         if self._graph_key != key:
             self._graph_key, self._graphed = key, None
             try:
-                sx = torch.zeros_like(x).requires_grad_(True)
                 ss = torch.ones(1, 1, device=x.device, dtype=x.dtype)
+                s0 = torch.zeros_like(x).requires_grad_(True)
                 l0 = profiling.launches()                  # launches of one eager forward / backward
-                out = self.model(sx, ss)
+                out = self.model(s0, ss)
                 l1 = profiling.launches()
-                torch.autograd.grad(out.sum(), sx)
+                torch.autograd.grad(out.sum(), s0)
                 self._graph_launches = (l1 - l0, profiling.launches() - l1)
+                del out, s0                                # no autograd node of the default stream may survive
+                torch.cuda.synchronize()
+                sx = torch.zeros_like(x).requires_grad_(True)
                 model = self.model
                 self._graphed = torch.cuda.make_graphed_callables(lambda a, b: model(a, b), (sx, ss))
             except Exception as exc:                       # noqa: BLE001 - any capture problem: stay eager
