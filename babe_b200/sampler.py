@@ -232,6 +232,9 @@ class BlindSamplerFused:
                 torch.cuda.synchronize()
                 sx = torch.zeros_like(x).requires_grad_(True)
                 model = self.model
+                quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+                if quiet is not None:                      # the capture runs on a side stream by design
+                    quiet(False)
                 self._graphed = torch.cuda.make_graphed_callables(lambda a, b: model(a, b), (sx, ss))
             except Exception as exc:                       # noqa: BLE001 - any capture problem: stay eager
                 warnings.warn(f"CUDA-graph capture of the denoiser failed ({exc!r}); running it eagerly")
