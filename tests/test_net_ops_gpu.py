@@ -121,3 +121,30 @@ def test_denoiser_fused_matches_composite():
     denoiser.FUSED = True
     assert rel_l2(outs[1][0], outs[0][0]) < 2e-5
     assert rel_l2(outs[1][1], outs[0][1]) < 1e-4
+
+
+def test_glue_matches_reference_golden(golden):
+    """The CUDA glue through the C ABI against vectors produced by the reference's own ResnetBlock /
+    UpDownResample (tests/golden/make_golden_net.py)."""
+    from babe_b200 import build, net_ops
+    from oracle.net_glue import CUBIC
+    build.build()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden("net_glue.npz")
+    c = lambda k: torch.from_numpy(g[k]).cuda()
+    x = c("blk_x").requires_grad_(True)
+    y = x
+    for i in range(2):
+        y = net_ops.res_layer(y, c(f"blk_gamma{i}"), c(f"blk_aff{i}"), c(f"blk_gate{i}"), c(f"blk_w{i}"),
+                              (2 ** i, 1), 8, 1e-7)
+    y = net_ops.add_scale(y, x)
+    gx, = torch.autograd.grad(y, x, c("blk_gy"))
+    assert rel_l2(y.detach().cpu(), g["blk_y"]) < 1e-5
+    assert rel_l2(gx.cpu(), g["blk_gx"]) < 1e-5
+    for name, up in (("down", False), ("up", True)):
+        xr = c(f"rs_{name}_x").requires_grad_(True)
+        yr = net_ops.resample2(xr, CUBIC, up)
+        gr, = torch.autograd.grad(yr, xr, c(f"rs_{name}_gy"))
+        assert rel_l2(yr.detach().cpu(), g[f"rs_{name}_y"]) < 1e-6
+        assert rel_l2(gr.cpu(), g[f"rs_{name}_gx"]) < 1e-6
