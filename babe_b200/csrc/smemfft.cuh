@@ -152,46 +152,6 @@ BABE_HD void stockham_stage(const float2* in, float2* out, int n, int stride, in
   }
 }
 
-// Odd-prime stage with one OUTPUT per task (R x more parallelism than one
-// butterfly per task, which leaves most of the CTA idle for R = 13..23):
-//   out[u] = sum_t in[t] W_n^{t (k step + u n/R)}
-// -- the stage twiddle and the DFT weight are one root lookup per term.
-template <int R>
-BABE_HD void stockham_stage_wide(const float2* in, float2* out, int n, int stride, int nseq,
-                                 int Ns, const float2* wn, int tid, int nthreads) {
-  const int m = n / R;
-  const int tw_step = n / (Ns * R);
-  const int nr = n / R;
-  const int tasks = nseq * n;
-  for (int q = tid; q < tasks; q += nthreads) {
-    const int seq = q / n, rem = q - seq * n;
-    const int u = rem / m, j = rem - u * m;          // consecutive threads: consecutive j
-    const int k = j % Ns;
-    int inc = k * tw_step + u * nr;
-    if (inc >= n) inc -= n;
-    const float2* src = in + seq * stride;
-    // all 2(R-1) shared-memory loads are issued before the multiply-adds (ILP)
-    float2 v[R], w[R];
-    v[0] = src[pad16(j)];
-    int idx = 0;
-#pragma unroll
-    for (int t = 1; t < R; ++t) {
-      idx += inc;
-      if (idx >= n) idx -= n;
-      v[t] = src[pad16(j + t * m)];
-      w[t] = wn[idx];
-    }
-    float2 acc = v[0], acc2 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int t = 1; t < R; ++t) {
-      float2& a = (t & 1) ? acc : acc2;               // two accumulation chains
-      a.x += v[t].x * w[t].x - v[t].y * w[t].y;
-      a.y += v[t].x * w[t].y + v[t].y * w[t].x;
-    }
-    out[seq * stride + pad16((j - k) * R + k + u * Ns)] = make_float2(acc.x + acc2.x, acc.y + acc2.y);
-  }
-}
-
 #ifdef __CUDA_ARCH__
 #define BABE_CTA_SYNC() __syncthreads()
 #else
