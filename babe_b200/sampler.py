@@ -436,6 +436,134 @@ class BlindSamplerFused:
             return x.detach(), data_denoised.detach(), data_score.detach(), t.detach()
         return x.detach()
 
+    # -- generic (non-blind) conditional sampling: any differentiable degradation ----------------
+    @staticmethod
+    def denoised2score(x_d0, x, t):
+        """testing/blind_bwe_sampler.py:503-505 (Tweedie)."""
+        return (x_d0 - x) / t ** 2
+
+    @staticmethod
+    def score2denoised(score, x, t):
+        """testing/blind_bwe_sampler.py:506-507."""
+        return score * t ** 2 + x
+
+    def apply_FIR_filter(self, y):
+        """testing/blind_bwe_sampler.py:211-218 on ``k_fir_filter`` (``self.filt``: the taps)."""
+        from . import bandwidth_extension as bwe
+        return bwe.apply_low_pass_firwin(y, self.filt)
+
+    @staticmethod
+    def prepare_smooth_mask(mask, size=10):
+        """testing/blind_bwe_sampler.py:232-257: hann ramps of ``size`` samples at every transition of the
+        first row's mask (before a gap: falling half, after a gap: rising half); all rows get that mask."""
+        hann = torch.hann_window(size * 2)
+        left, right = hann[:size].to(mask), hann[size:].to(mask)
+        B = mask.shape[0]
+        m = mask[0]
+        new = m.clone()
+        mh = m.detach().cpu()
+        change = torch.nonzero(mh[1:] != mh[:-1]).reshape(-1) + 1
+        if mh[0] != 1:                                   # the reference starts with prev = 1
+            change = torch.cat((torch.zeros(1, dtype=change.dtype), change))
+        for i in change.tolist():
+            if mh[i] == 0:
+                new[i - size:i] = right
+            if mh[i] == 1:
+                new[i:i + size] = left
+        return new.unsqueeze(0).expand(B, -1)
+
+    def _generic_rec_grads(self, x_den, y, x_in, t_in, degradation):
+        """get_rec_grads (:75-135) for an arbitrary differentiable degradation (2-norm branch)."""
+        ps = self.args.tester.posterior_sampling
+        if ps.SNR_observations != "None" or ps.stft_distance.use or ps.norm not in (1, 2, "fro"):
+            raise NotImplementedError("generic degradations support the plain 1-/2-norm guidance")
+        norm = torch.linalg.norm(y - degradation(x_den), dim=1, ord=ps.norm)
+        (g,) = torch.autograd.grad(outputs=norm.sum(), inputs=x_in)
+        normguide = torch.linalg.norm(g) / self.args.exp.audio_len ** 0.5
+        return self.xi / (normguide + 1e-6) * g / t_in
+
+    def get_score(self, x, y, t_i, degradation, dc_step=None):
+        """testing/blind_bwe_sampler.py:160-209.  ``dc_step(x_hat)``: optional data-consistency step."""
+        if y is None:
+            with torch.no_grad():
+                return self.denoised2score(self.get_denoised_estimate(x, t_i), x, t_i)
+        if self.xi > 0:
+            x = x.detach().requires_grad_(True)
+            x_den = self.get_denoised_estimate(x, t_i)
+            rec = self._generic_rec_grads(x_den, y, x, t_i, degradation)
+            x = x.detach()
+            score = self.denoised2score(x_den.detach(), x, t_i) - rec
+            if dc_step is not None:
+                score = self.denoised2score(dc_step(self.score2denoised(score, x, t_i)), x, t_i)
+            return score
+        with torch.no_grad():
+            x_hat = self.diff_params.denoiser(x, self.model, t_i.unsqueeze(-1))     # :192 (no DC/Nyquist filter)
+            if dc_step is not None:
+                x_hat = dc_step(x_hat)
+            return self.denoised2score(x_hat, x, t_i)
+
+    def predict_conditional(self, y, degradation, rid=False, dc_step=None):
+        """testing/blind_bwe_sampler.py:387-497 (``predict`` with observations y)."""
+        shape, device = y.shape, y.device
+        if self.start_sigma is None:
+            t = self.diff_params.create_schedule(self.nb_steps).to(device)
+            x = self._randn(shape, device) * t[0]
+        else:
+            t = self.diff_params.create_schedule_from_initial_t(self.start_sigma, self.nb_steps).to(device)
+            x = y + self._randn(shape, device) * t[0]
+        gamma = self.diff_params.get_gamma(t).to(device)
+        t_host = t.cpu()
+        if rid:
+            data_denoised = torch.zeros((self.nb_steps, shape[0], shape[1]))
+            data_score = torch.zeros((self.nb_steps, shape[0], shape[1]))
+        for i in range(self.nb_steps):
+            x_hat, t_hat = self.move_timestep(x, t[i], gamma[i], self.diff_params.Snoise)
+            score = self.get_score(x_hat, y, t_hat, degradation, dc_step)
+            d = -t_hat * score
+            if rid:
+                data_denoised[i] = self.score2denoised(score, x_hat, t_hat)
+                data_score[i] = score
+            h = t[i + 1] - t_hat
+            if float(t_host[i + 1]) != 0 and self.order == 2:
+                t_prime = t[i + 1]
+                x_prime = x_hat + h * d
+                score = self.get_score(x_prime, y, t_prime, degradation, dc_step)
+                x = x_hat + h * ((1 / 2) * d + (1 / 2) * (-t_prime * score))
+            else:
+                x = x_hat + h * d
+        if rid:
+            return x.detach(), data_denoised.detach(), data_score.detach(), t.detach()
+        return x.detach()
+
+    def predict_bwe_AR(self, ylpf, y_masked, filt, filt_type, rid=False, test_filter_fit=False,
+                       compute_sweep=False, mask=None):
+        """testing/blind_bwe_sampler.py:259-303: bandwidth extension of a segment whose head (mask = 1)
+        is already known from the previous segment: y = mask y_masked + (1 - mask) ylpf, degradation
+        x -> mask x + (1 - mask) A(x); with ``complete_recording.inpaint_DC`` the known part is also
+        enforced by a data-consistency step through a hann-smoothed mask."""
+        assert mask is not None
+        if test_filter_fit or compute_sweep:
+            raise NotImplementedError("test_filter_fit / compute_sweep logging on the AR path")
+        device = ylpf.device
+        mask = mask.to(device)
+        if filt_type == "fc_A":
+            self.freqs = torch.fft.rfftfreq(self.args.tester.blind_bwe.NFFT, d=1 / self.args.exp.sample_rate).to(device)
+            self.params = filt.to(device)
+            lowpass = lambda x: self.apply_filter_fcA(x, self.params)
+        elif filt_type == "firwin":
+            self.filt = filt.to(device)
+            lowpass = self.apply_FIR_filter
+        else:
+            raise NotImplementedError(filt_type)
+        y = mask * y_masked + (1 - mask) * ylpf
+        degradation = lambda x: mask * x + (1 - mask) * lowpass(x)
+        dc_step = None
+        if self.args.tester.complete_recording.inpaint_DC:
+            smooth = self.prepare_smooth_mask(mask, 50)
+            y_smooth = smooth * y_masked
+            dc_step = lambda x_hat: y_smooth + x_hat - smooth * x_hat     # data_consistency_step_classic (:63-73)
+        return self.predict_conditional(y, degradation, rid, dc_step)
+
     def predict_bwe(self, ylpf, filt, filt_type, rid=False, test_filter_fit=False, compute_sweep=False):
         """testing/blind_bwe_sampler.py:306-364, the ``fc_A`` branch (known
         parametric filter, no re-estimation).  The classical FIR/IIR observation

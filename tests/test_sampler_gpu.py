@@ -161,3 +161,24 @@ def test_non_blind_and_unconditional(golden):
         s.predict_bwe(y.clone(), filt, "cheby1")
     xu = s.predict_unconditional(tuple(y.shape), y.device)
     assert xu.shape == y.shape and torch.isfinite(xu).all()
+
+
+def test_predict_bwe_AR_and_bwe_match_reference(golden):
+    """Non-blind and autoregressive sampling (testing/blind_bwe_sampler.py:259-364, 406-497) on the CUDA
+    operators against trajectories of the UNMODIFIED reference sampler (tests/golden/make_golden_ar.py)."""
+    from babe_b200 import build
+    build.build()
+    from babe_b200 import edm, sampler
+    g = golden("sampler_ar.npz")
+    c = lambda k: torch.from_numpy(g[k]).cuda()
+    args = sampler.make_args(sample_rate=int(g["sr"]), audio_len=g["x"].shape[1], T=4, NFFT=int(g["nfft"]),
+                             max_iter=20)
+    model = ToyDenoiser().cuda()
+    s = sampler.BlindSamplerFused(model, edm.EDM(args), args, rid=False)
+    torch.manual_seed(77)
+    x = s.predict_bwe_AR(c("ylpf"), c("y_masked"), c("filt"), "fc_A", mask=c("mask"))
+    assert rel_l2(x.cpu(), g["x_ar"]) < 1e-3
+    s2 = sampler.BlindSamplerFused(model, edm.EDM(args), args, rid=False)
+    torch.manual_seed(78)
+    xb = s2.predict_bwe(c("ylpf"), c("filt"), "fc_A")
+    assert rel_l2(xb.cpu(), g["x_bwe"]) < 1e-3
