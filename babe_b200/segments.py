@@ -87,3 +87,73 @@ def restore_recording(sampler, degraded, seg_len, ola=256, discard_end=200, join
     all_filt = bd.gather_rows(filts)
     final = merge(all_pred, spans, degraded.shape[-1], ola, discard_end)
     return final, [(spans[s], all_filt[s]) for s in range(len(spans))]
+
+
+def restore_recording_ar(sampler, degraded, seg_len, sample_rate, overlap_s=0.25, n_segments_blindstep=2,
+                         ix_start_s=0, std=0.1, typefilter="fc_A", discard_end=200, discard_start=0,
+                         rng=None, estimated_filter=None):
+    """Autoregressive restoration of a whole recording with ONE filter estimated once:
+    ``BlindTester.test_real_blind_bwe_complete`` (testing/blind_bwe_tester.py:710-867) without file
+    I/O, resampling and wandb.
+
+    1. the recording is normalised to ``std`` (:746-747);
+    2. blind step on ``n_segments_blindstep`` randomly placed windows (:757-777) -> filter estimate
+       (skipped when ``estimated_filter`` is given);
+    3. first window with ``predict_bwe`` (:799-805), then windows advancing by
+       ``seg_len - overlap - discard_end`` samples with ``predict_bwe_AR``: the first ``overlap`` samples of
+       each window are known from the previous prediction (mask = 1 there, :807-838);
+    4. last, zero padded window (:841-859), scale restored (:861).
+
+    Sequential by construction (each window needs the previous prediction): replicas only across
+    recordings.  ``degraded``: (1, L) tensor on the sampler's device.  Returns
+    (restored (1, L), filter (2, K))."""
+    import numpy as np
+    segL = int(seg_len)
+    L = degraded.shape[-1]
+    scale = degraded.std(-1)
+    degraded = std * degraded / scale.unsqueeze(-1)
+    ix_first = int(sample_rate * ix_start_s)
+    final = torch.zeros_like(degraded)
+    if estimated_filter is None:
+        if n_segments_blindstep == 1:
+            y = degraded[..., ix_first:ix_first + segL]
+        else:
+            rng = rng if rng is not None else np.random
+            y = degraded[..., ix_first:ix_first + segL].repeat(n_segments_blindstep, 1)
+            for j in range(n_segments_blindstep):
+                ix = int(rng.randint(0, L - segL))
+                y[j] = degraded[0, ix:ix + segL]
+        pred, estimated_filter = sampler.predict_blind_bwe(y, rid=False)
+        final[0, ix_first:ix_first + segL] = pred[0]
+    overlap = int(overlap_s * sample_rate)
+    keep = segL - discard_end
+    ix = 0
+    seg = degraded[..., ix:ix + segL]
+    pred = sampler.predict_bwe(seg, estimated_filter, typefilter, rid=False)
+    previous = pred[..., :keep]
+    final[..., ix:ix + keep] = previous
+    ix += segL - overlap - discard_end
+    y_masked = torch.zeros_like(pred)
+    mask = torch.ones_like(seg)
+    mask[..., overlap:] = 0
+    # the reference stops at ix >= L - segL - discard_end (:820) and then fails on a remainder longer than one
+    # window (:852-859); full windows are processed here as long as more than one window is left
+    while ix < L - segL - discard_end - discard_start or L - ix > segL:
+        y_masked[..., :overlap] = previous[..., segL - overlap - discard_end:]
+        seg = degraded[..., ix:ix + segL]
+        pred = sampler.predict_bwe_AR(seg, y_masked, estimated_filter, typefilter, rid=False, mask=mask)
+        previous = pred[..., :keep]
+        final[..., ix:ix + keep] = previous
+        ix += segL - overlap - discard_end
+    seg = degraded[..., ix:]
+    n = seg.shape[-1]
+    y_masked[..., :overlap] = pred[..., -overlap:]          # sic (:842): the tail of the FULL last prediction
+    if n < segL:
+        seg_zp = torch.cat((seg, seg.new_zeros((1, segL - n))), -1)
+        y_masked[..., n:segL] = 0                            # the padding is "observed" silence (:848-850)
+        mask[..., n:segL] = 0
+    else:
+        seg_zp = seg[..., :segL]
+    pred = sampler.predict_bwe_AR(seg_zp, y_masked, estimated_filter, typefilter, rid=False, mask=mask)
+    final[..., ix:ix + n] = pred[..., :n]
+    return final * scale.unsqueeze(-1) / std, estimated_filter
