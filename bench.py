@@ -515,13 +515,25 @@ def run_operator_sweep(a):
         out = torch.empty_like(x)
         fit = sampler.FilterFit(nfft=NFFT, sample_rate=SR, device=dev)
         p = torch.tensor([[280.0, 285, 290, 295, 300], [-15.0, -17, -20, -25, -30]], device=dev)
+        fp = torch.stack((fc, A))
+        spec_bytes = 8 * B * (NFFT // 2 + 1) * ops.num_frames(T, NFFT)
+
+        def recg(x=x, y=y, fp=fp):
+            xg = x.detach().requires_grad_(True)
+            n = sampler.rec_guidance_norms(xg, y, f, fp, NFFT)
+            torch.autograd.grad(n.sum(), xg)
+
         cases = {
             "apply_filter fwd (8BT)": (lambda: ops.apply_filter(x, NFFT, freqs=f, fc=fc, A=A, out=out), 8 * B * T),
             "apply_filter adj (8BT)": (lambda: ops.apply_filter(x, NFFT, freqs=f, fc=fc, A=A, adjoint=True, out=out), 8 * B * T),
             "fit statistics (8BT)": (lambda: ops.stft_stats(x, y, NFFT), 8 * B * T),
             "fit loop 100 it": (lambda: fit(x, y, p.clone(), abc=abc), 0),
+            "rec-guidance norms + grad (20BT, r materialised)": (recg, 20 * B * T),
+            "apply_stft a1 (4BT + 8BFM)": (lambda: ops.stft(x, NFFT), 4 * B * T + spec_bytes),
+            "apply_filter_istft a2 (8BFM + 4BT)": (lambda: ops.istft(X, NFFT), 4 * B * T + spec_bytes),
         }
         abc = ops.stft_stats(x, y, NFFT)
+        X = ops.stft(x, NFFT)
         for name, (fn, nbytes) in cases.items():
             for _ in range(3):
                 fn()
