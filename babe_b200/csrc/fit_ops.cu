@@ -125,7 +125,7 @@ struct FitArgs {
 };
 
 __global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) {
-  // Per iteration (2 CTA barriers):
+  // Per iteration (3 CTA barriers):
   //  (A) every thread evaluates its bins: H_k, the loss term and u_k = (norm dnorm/dH_k) H_k, into
   //      shared memory;
   //  (B) warp (q, s) sums quantity q (segment q's u and u*log2(f/fc_q), or the loss) over bin slice s,
