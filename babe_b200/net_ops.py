@@ -13,6 +13,7 @@ activations only: the functions are used when the parameters are frozen (samplin
 ``denoiser.py`` falls back to the composite PyTorch expression otherwise.
 """
 import ctypes
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -97,20 +98,25 @@ def _rows(t, N, C):
 # dgrad kernel takes 0.39 ms and the fprop kernel 0.99 ms on B200, at 8 x 64 x 64 x 2048 they
 # are equal), so both are timed once per (shape, dilation) and the faster one is kept.
 # ---------------------------------------------------------------------------
-_FLIPPED = {}
+_FLIPPED = {}          # id(weight object) -> (weakref to it, its version, flipped-transposed copy)
 _CONV_CHOICE = {}
 AUTOTUNE_CONV = True
 
 
 def _flipped(weight):
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
-    hit = _FLIPPED.get(key)
-    if hit is None:
-        if len(_FLIPPED) > 4096:
-            _FLIPPED.clear()
-        hit = weight.detach().transpose(0, 1).flip(2, 3).contiguous()
-        _FLIPPED[key] = hit
-    return hit
+    """W^T flipped for ``weight`` (the caller's persistent tensor object, e.g. the nn.Parameter), cached
+    per OBJECT: the entry is valid while that very object is alive and its version counter unchanged,
+    and is dropped when the object dies -- a recycled address or id can never return a stale copy."""
+    k = id(weight)
+    ent = _FLIPPED.get(k)
+    if ent is not None and ent[0]() is weight and ent[1] == weight._version:
+        return ent[2]
+    flipped = weight.detach().transpose(0, 1).flip(2, 3).contiguous()
+
+    def _drop(_, k=k):
+        _FLIPPED.pop(k, None)
+    _FLIPPED[k] = (weakref.ref(weight, _drop), weight._version, flipped)
+    return flipped
 
 
 def _time(fn):
@@ -125,16 +131,18 @@ def _time(fn):
     return s.elapsed_time(e)
 
 
-def conv_same(inp, weight, pad, dilation, transposed=False):
-    """transposed=False: conv2d(inp, weight); True: its input-gradient for grad_output = inp."""
+def conv_same(inp, weight, pad, dilation, transposed=False, wobj=None):
+    """transposed=False: conv2d(inp, weight); True: its input-gradient for grad_output = inp.
+    ``wobj``: the persistent tensor object ``weight`` was detached from (cache key of the flipped copy)."""
+    wobj = weight if wobj is None else wobj
     if transposed:
         size = (inp.shape[0], weight.shape[1], inp.shape[2], inp.shape[3])
         direct = lambda: torch.nn.grad.conv2d_input(size, weight, inp, 1, pad, dilation)
-        other = lambda: F.conv2d(inp, _flipped(weight), None, 1, pad, dilation)
+        other = lambda: F.conv2d(inp, _flipped(wobj), None, 1, pad, dilation)
     else:
         size = (inp.shape[0], weight.shape[0], inp.shape[2], inp.shape[3])
         direct = lambda: F.conv2d(inp, weight, None, 1, pad, dilation)
-        other = lambda: torch.nn.grad.conv2d_input(size, _flipped(weight), inp, 1, pad, dilation)
+        other = lambda: torch.nn.grad.conv2d_input(size, _flipped(wobj), inp, 1, pad, dilation)
     if not AUTOTUNE_CONV:
         return direct()
     key = (tuple(inp.shape), tuple(weight.shape), tuple(dilation), transposed, inp.device.index)
@@ -152,15 +160,16 @@ class _ResLayer(torch.autograd.Function):
         N, C = x.shape[:2]
         gamma = gamma.detach().reshape(-1).contiguous().float()
         aff, gate = _rows(aff, N, C), _rows(gate, N, C)
-        weight = weight.detach()
+        wobj, weight = weight, weight.detach()
         pad = _same_padding(weight, dilation)
         part, S = gn_stats(x, groups)
         h = gn_film_gelu(x, part, S, gamma, aff, groups, eps)
-        v = conv_same(h, weight, pad, dilation)
+        v = conv_same(h, weight, pad, dilation, wobj=wobj)
         del h
         y = gate_residual(x, v, gate)
         ctx.save_for_backward(x, part, gamma, aff, gate, weight)
         ctx.cfg = (S, dilation, groups, eps, pad)
+        ctx.wobj = wobj                      # the caller's weight object: key of the flipped-copy cache
         return y
 
     @staticmethod
@@ -169,7 +178,7 @@ class _ResLayer(torch.autograd.Function):
         S, dilation, groups, eps, pad = ctx.cfg
         gy = gy.contiguous()
         gv = gate_residual(None, gy, gate)
-        gh = conv_same(gv, weight, pad, dilation, transposed=True)
+        gh = conv_same(gv, weight, pad, dilation, transposed=True, wobj=ctx.wobj)
         del gv
         gx = gn_film_gelu_bwd(gh.contiguous(), x, gy, part, S, gamma, aff, groups, eps)
         return gx, None, None, None, None, None, None, None
@@ -181,17 +190,18 @@ class _ConvSame(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, dilation):
-        weight = weight.detach()
+        wobj, weight = weight, weight.detach()
         pad = _same_padding(weight, dilation)
         ctx.save_for_backward(weight)
         ctx.cfg = (dilation, pad)
-        return conv_same(x.contiguous(), weight, pad, dilation)
+        ctx.wobj = wobj
+        return conv_same(x.contiguous(), weight, pad, dilation, wobj=wobj)
 
     @staticmethod
     def backward(ctx, g):
         weight, = ctx.saved_tensors
         dilation, pad = ctx.cfg
-        return conv_same(g.contiguous(), weight, pad, dilation, transposed=True), None, None
+        return conv_same(g.contiguous(), weight, pad, dilation, transposed=True, wobj=ctx.wobj), None, None
 
 
 def _pair(d):
@@ -219,7 +229,8 @@ def _frozen(*ts):
 
 def usable(x, *params):
     """The fused path applies to CUDA float32 activations with frozen parameters."""
-    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and _frozen(*params)
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and _frozen(*params)
+            and x.shape[0] * x.shape[1] <= 65535)          # one grid row per (n, c) plane
 
 
 def res_layer(x, gamma, aff, gate, weight, dilation, groups, eps):
