@@ -217,7 +217,11 @@ class BlindSamplerFused:
     def _graphed_model(self, x):
         """The network as a callable replaying captured CUDA graphs (``torch.cuda.make_graphed_callables``:
         one graph for the forward, one for the backward wrt the input); eager model on any failure."""
-        key = (tuple(x.shape), x.dtype, x.device)
+        try:      # in-place weight updates (load_state_dict) invalidate what the graphs captured
+            ver = sum(p._version for p in self.model.parameters())
+        except Exception:                                  # noqa: BLE001 - not an nn.Module
+            ver = 0
+        key = (tuple(x.shape), x.dtype, x.device, ver)
         if self._graph_key != key:
             self._graph_key, self._graphed = key, None
             try:

@@ -67,3 +67,16 @@ def test_smooth_mask_literal():
     m = torch.ones(3, 300)
     m[:, 120:] = 0
     assert torch.equal(S.prepare_smooth_mask(m, 50), literal(m, 50))
+
+
+def test_cuda_graph_option_falls_back_to_eager_without_cuda(golden):
+    """``cuda_graph=True`` must never break sampling: any capture problem -> eager model + a warning."""
+    import pytest
+    g = golden("sampler_ar.npz")
+    s, args = _sampler(g)
+    s.cuda_graph = True
+    x = torch.zeros(2, 64, requires_grad=True)
+    with pytest.warns(UserWarning, match="capture of the denoiser failed"):
+        net = s._graphed_model(x)
+    assert net is s.model
+    assert s._graphed_model(x) is s.model                      # cached decision, no second attempt
