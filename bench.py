@@ -253,7 +253,8 @@ def run_ours(a):
     if dom:
         o = ops[dom]
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(o["gbs"], 1), "peak": peak, "unit": "GB/s",
-                "frac": round(o["gbs"] / peak, 4), "traffic": traffic,
+                "frac": round(o["gbs"] / peak, 4), "frac_of_nominal_8TBps": round(o["gbs"] / 8000.0, 4),
+                "traffic": traffic,
                 "algorithmic_bytes": int(o["bytes_avg"]), "peak_source": peak_src,
                 "avg_ms": round(o["ms_avg"], 4), "calls": o["calls"],
                 "share_of_step": round(o["ms_total"] / prof_run["ms"], 4),
