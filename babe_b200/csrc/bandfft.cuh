@@ -23,7 +23,7 @@ template <int R3>
 struct BandCore {
   static constexpr int M = 256 * R3, TPB = 16 * R3, ROW = TPB + 1, EX = 16 * ROW, NP = 16 / R3;
   struct Regs { float wr[16], wi[16]; };                      // W_M^{t k1}
-  __device__ static __forceinline__ void init_regs(Regs& r, const float2* roots_m, int t) {
+  BABE_HD static void init_regs(Regs& r, const float2* roots_m, int t) {
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
       const float2 w = roots_m[t * k1];
@@ -34,24 +34,28 @@ struct BandCore {
   __device__ static __forceinline__ void load_twiddles(float2* tw, const float2* roots_m) {
     for (int i = threadIdx.x; i < TPB; i += blockDim.x) tw[i] = roots_m[16 * i];
   }
-  __device__ static __forceinline__ void fwd(float (&re)[16], float (&im)[16], float2* ex,
-                                             const float2* tw, const Regs& rg, int t) {
+  // The three passes as per-thread functions (also callable on the host, where a test runs the
+  // "threads" of one band one after the other: tests/host/bandfft_host_check.cu).
+  BABE_HD static void pass1(float (&re)[16], float (&im)[16], float2* ex, const Regs& rg, int t) {
     fft16_split(re, im);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1)
       ex[k1 * ROW + t] = make_float2(re[k1] * rg.wr[k1] - im[k1] * rg.wi[k1],
                                      re[k1] * rg.wi[k1] + im[k1] * rg.wr[k1]);
-    __syncthreads();
-    {
-      float2* col = ex + (t & 15) * ROW + (t >> 4);          // + R3 n2
+  }
+  // reads its column of ex, transforms it; for R3 > 1 the result goes back in place (call pass2_store
+  // after ALL threads have run pass2_load when emulating on the host: the columns are disjoint, so the
+  // device code stores immediately)
+  BABE_HD static void pass2(float (&re)[16], float (&im)[16], float2* ex, int t) {
+    float2* col = ex + (t & 15) * ROW + (t >> 4);            // + R3 n2
 #pragma unroll
-      for (int n2 = 0; n2 < 16; ++n2) { const float2 v = col[R3 * n2]; re[n2] = v.x; im[n2] = v.y; }
-      fft16_split(re, im);
-      if (R3 == 1) return;                                    // X[t + 16 k2]
+    for (int n2 = 0; n2 < 16; ++n2) { const float2 v = col[R3 * n2]; re[n2] = v.x; im[n2] = v.y; }
+    fft16_split(re, im);
+    if (R3 == 1) return;                                      // X[t + 16 k2]
 #pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) col[R3 * k2] = make_float2(re[k2], im[k2]);
-    }
-    __syncthreads();
+    for (int k2 = 0; k2 < 16; ++k2) col[R3 * k2] = make_float2(re[k2], im[k2]);
+  }
+  BABE_HD static void pass3(float (&re)[16], float (&im)[16], const float2* ex, const float2* tw, int t) {
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const int k2 = (t >> 4) + R3 * j;
@@ -71,15 +75,24 @@ struct BandCore {
       for (int k3 = 0; k3 < R3; ++k3) { re[j * R3 + k3] = ar[k3]; im[j * R3 + k3] = ai[k3]; }
     }
   }
+  __device__ static __forceinline__ void fwd(float (&re)[16], float (&im)[16], float2* ex,
+                                             const float2* tw, const Regs& rg, int t) {
+    pass1(re, im, ex, rg, t);
+    __syncthreads();
+    pass2(re, im, ex, t);
+    if (R3 == 1) return;
+    __syncthreads();
+    pass3(re, im, ex, tw, t);
+  }
   // slot of output register r
-  __device__ static __forceinline__ int out_slot(int r, int t) { return t + TPB * (r / R3) + 256 * (r % R3); }
+  BABE_HD static int out_slot(int r, int t) { return t + TPB * (r / R3) + 256 * (r % R3); }
 
  private:
-  __device__ static __forceinline__ void small_fft(float (&r)[1], float (&i)[1]) {}
-  __device__ static __forceinline__ void small_fft(float (&r)[2], float (&i)[2]) { fft2(r, i); }
-  __device__ static __forceinline__ void small_fft(float (&r)[4], float (&i)[4]) { fft4(r, i); }
-  __device__ static __forceinline__ void small_fft(float (&r)[8], float (&i)[8]) { fft8(r, i); }
-  __device__ static __forceinline__ void small_fft(float (&r)[16], float (&i)[16]) { fft16_split(r, i); }
+  BABE_HD static void small_fft(float (&r)[1], float (&i)[1]) {}
+  BABE_HD static void small_fft(float (&r)[2], float (&i)[2]) { fft2(r, i); }
+  BABE_HD static void small_fft(float (&r)[4], float (&i)[4]) { fft4(r, i); }
+  BABE_HD static void small_fft(float (&r)[8], float (&i)[8]) { fft8(r, i); }
+  BABE_HD static void small_fft(float (&r)[16], float (&i)[16]) { fft16_split(r, i); }
 };
 
 }  // namespace babe

@@ -24,3 +24,19 @@ def test_fft_building_blocks_on_host(tmp_path):
     assert len(rows) == 27
     for name, n, err in rows:
         assert float(err) < 2e-6, (name, n, err)        # fp32 transforms of <= 2048 points
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_band_core_passes_on_host(tmp_path):
+    """BandCore<R3> (csrc/bandfft.cuh): the three passes the CQT band kernels call, emulated thread by
+    thread on the host, for M = 256 ... 4096."""
+    exe = str(tmp_path / "bandfft_host_check")
+    src = os.path.join(ROOT, "tests", "host", "bandfft_host_check.cu")
+    cmd = [NVCC, "-O1", "-std=c++17", "-o", exe, src, "-I", os.path.join(ROOT, "babe_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include")]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout
+    rows = [l.split() for l in out.strip().splitlines()]
+    assert [int(r[1]) for r in rows] == [256, 512, 1024, 2048, 4096]
+    for name, n, err in rows:
+        assert float(err) < 2e-6, (name, n, err)
