@@ -40,3 +40,17 @@ def test_band_core_passes_on_host(tmp_path):
     assert [int(r[1]) for r in rows] == [256, 512, 1024, 2048, 4096]
     for name, n, err in rows:
         assert float(err) < 2e-6, (name, n, err)
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_core3_passes_on_host(tmp_path):
+    """Core3 (csrc/stft_cores.cuh): forward / mirror / inverse passes of the 4096-point core of
+    k_apply_filter, k_stft_stats and k_fir_filter, emulated thread by thread on the host."""
+    exe = str(tmp_path / "core3_host_check")
+    src = os.path.join(ROOT, "tests", "host", "core3_host_check.cu")
+    cmd = [NVCC, "-O1", "-std=c++17", "-o", exe, src, "-I", os.path.join(ROOT, "babe_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include")]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout
+    vals = dict(l.split() for l in out.strip().splitlines())
+    assert float(vals["fwd"]) < 5e-7 and float(vals["roundtrip"]) < 5e-7 and float(vals["mirror"]) == 0.0
