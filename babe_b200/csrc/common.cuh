@@ -6,6 +6,10 @@
 
 #include "babe_b200.h"
 
+#ifndef BABE_HD
+#define BABE_HD __host__ __device__ __forceinline__
+#endif
+
 namespace babe {
 
 void set_error(const char* fmt, ...);

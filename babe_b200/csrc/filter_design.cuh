@@ -21,13 +21,32 @@ struct FilterSegs {
   int bad;                            // some fc[i>=1] above the last bin (reference: IndexError)
 };
 
-__device__ __forceinline__ float seg_gain(float A, float fc, float f) {
+// Round-to-nearest fp32 division / product that the compiler may not contract or approximate; on the
+// host (tests/host/filter_design_host_check.cu) plain IEEE operations through volatiles.
+BABE_HD float rn_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdiv_rn(a, b);
+#else
+  volatile float q = a / b;
+  return q;
+#endif
+}
+BABE_HD float rn_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  volatile float q = a * b;
+  return q;
+#endif
+}
+
+BABE_HD float seg_gain(float A, float fc, float f) {
   // 10 ** (A * log2(f / fc) / 20)
-  const float t = __fdiv_rn(__fmul_rn(A, log2f(__fdiv_rn(f, fc))), 20.0f);
+  const float t = rn_div(rn_mul(A, log2f(rn_div(f, fc))), 20.0f);
   return exp10f(t);
 }
 
-__device__ __forceinline__ int first_bin_ge(const float* f, int F, float v) {
+BABE_HD int first_bin_ge(const float* f, int F, float v) {
   // f is non-decreasing; NaN v -> F
   int lo = 0, hi = F;
   while (lo < hi) {
@@ -38,7 +57,7 @@ __device__ __forceinline__ int first_bin_ge(const float* f, int F, float v) {
 }
 
 // Executed by ONE thread.  f may live in shared or global memory.
-__device__ inline void build_segments(FilterSegs& s, const float* fc, const float* A, int K,
+__host__ __device__ inline void build_segments(FilterSegs& s, const float* fc, const float* A, int K,
                                       const float* f, int F) {
   s.K = K;
   s.bad = 0;
@@ -56,7 +75,7 @@ __device__ inline void build_segments(FilterSegs& s, const float* fc, const floa
     if (i == 0 || p < 0) {
       s.anchor[i] = 1.0f;
     } else {
-      s.anchor[i] = __fmul_rn(seg_gain(s.A[p], s.fc[p], f[s.kf[i]]), s.anchor[p]);
+      s.anchor[i] = rn_mul(seg_gain(s.A[p], s.fc[p], f[s.kf[i]]), s.anchor[p]);
     }
   }
 }
@@ -93,7 +112,7 @@ __device__ inline void build_segments_coop(FilterSegs& s, float* fkf /*shared, K
   __syncthreads();
 }
 
-__device__ __forceinline__ int bin_owner(const FilterSegs& s, int k) {
+BABE_HD int bin_owner(const FilterSegs& s, int k) {
   int o = -1;
 #pragma unroll 4
   for (int i = 0; i < s.K; ++i)
@@ -101,11 +120,11 @@ __device__ __forceinline__ int bin_owner(const FilterSegs& s, int k) {
   return o;
 }
 
-__device__ __forceinline__ float bin_gain(const FilterSegs& s, int k, float fk) {
+BABE_HD float bin_gain(const FilterSegs& s, int k, float fk) {
   const int o = bin_owner(s, k);
   if (o < 0) return 1.0f;
   const float g = seg_gain(s.A[o], s.fc[o], fk);
-  return (o == 0) ? g : __fmul_rn(g, s.anchor[o]);
+  return (o == 0) ? g : rn_mul(g, s.anchor[o]);
 }
 
 }  // namespace babe

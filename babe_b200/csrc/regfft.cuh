@@ -6,7 +6,9 @@
 #pragma once
 #include "fft_consts.cuh"
 
+#ifndef BABE_HD
 #define BABE_HD __host__ __device__ __forceinline__
+#endif
 
 namespace babe {
 

@@ -54,3 +54,41 @@ def test_core3_passes_on_host(tmp_path):
     out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout
     vals = dict(l.split() for l in out.strip().splitlines())
     assert float(vals["fwd"]) < 5e-7 and float(vals["roundtrip"]) < 5e-7 and float(vals["mirror"]) == 0.0
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_filter_design_device_logic_on_host(tmp_path, golden):
+    """csrc/filter_design.cuh (what k_design_filter and the fused kernels run: breakpoint search, anchor
+    chain through the parents, bin ownership, the reference's fp32 operation order) executed on the host
+    against H vectors produced by the reference's design_filter (tests/golden/operator_*.npz), including
+    the duplicate-bin / last-bin case and the scalar branch."""
+    import numpy as np
+    exe = str(tmp_path / "filter_design_host_check")
+    src = os.path.join(ROOT, "tests", "host", "filter_design_host_check.cu")
+    cmd = [NVCC, "-O1", "-std=c++17", "-o", exe, src, "-I", os.path.join(ROOT, "babe_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include")]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+
+    def run(f, fc, A):
+        fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+        with open(fin, "wb") as fh:
+            np.asarray([f.size, fc.size], dtype=np.int32).tofile(fh)
+            f.astype(np.float32).tofile(fh)
+            fc.astype(np.float32).tofile(fh)
+            A.astype(np.float32).tofile(fh)
+        subprocess.run([exe, fin, fout], check=True, timeout=60)
+        raw = np.fromfile(fout, dtype=np.float32)
+        return raw[:f.size], int(raw[f.size:].view(np.int32)[0])
+
+    for tag in ("operator_n1024.npz", "operator_n4096.npz"):
+        g = golden(tag)
+        f = g["f"]
+        H, bad = run(f, g["fc"], g["A"])
+        assert bad == 0 and np.linalg.norm(H - g["H"]) / np.linalg.norm(g["H"]) < 2e-6
+        H, bad = run(f, g["fc_dup"], g["A_dup"])
+        assert bad == 0 and np.linalg.norm(H - g["H_dup"]) / np.linalg.norm(g["H_dup"]) < 2e-6
+        H, bad = run(f, np.asarray([1000.0]), np.asarray([-20.0]))
+        assert np.linalg.norm(H - g["H_list"]) / np.linalg.norm(g["H_list"]) < 2e-6
+    # a breakpoint above the last bin: flagged (the reference raises IndexError there)
+    _, bad = run(g["f"], np.asarray([500.0, 1e6]), np.asarray([-10.0, -20.0]))
+    assert bad == 1
