@@ -127,4 +127,27 @@ BABE_HD float bin_gain(const FilterSegs& s, int k, float fk) {
   return (o == 0) ? g : rn_mul(g, s.anchor[o]);
 }
 
+// Chain rule of the design through the anchors.  Inputs: per-segment sums
+//   s[i] = sum of u_k over the bins owned by i,  l[i] = sum of u_k log2(f_k / fc_i),  u_k = dL/dH_k * H_k.
+// Executed by ONE thread.
+BABE_HD void finish_param_grads(const FilterSegs& sg, const float* f, int F,
+                                                   const double* s, const double* l,
+                                                   double* gfc, double* gA) {
+  const double alpha = 0.11512925464970229;   // ln(10)/20
+  const double ln2 = 0.6931471805599453;
+  for (int i = 0; i < sg.K; ++i) { gfc[i] = 0.0; gA[i] = 0.0; }
+  for (int i = 0; i < sg.K; ++i) {
+    if (sg.kf[i] >= F) continue;                 // owns no bin, s[i] = l[i] = 0
+    gA[i] += alpha * l[i];
+    gfc[i] += -alpha * (double)sg.A[i] / ((double)sg.fc[i] * ln2) * s[i];
+    int c = i;
+    while (sg.parent[c] >= 0) {
+      const int j = sg.parent[c];
+      gA[j] += alpha * (double)log2f(rn_div(f[sg.kf[c]], sg.fc[j])) * s[i];
+      gfc[j] += -alpha * (double)sg.A[j] / ((double)sg.fc[j] * ln2) * s[i];
+      c = j;
+    }
+  }
+}
+
 }  // namespace babe

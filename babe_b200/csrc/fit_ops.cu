@@ -60,26 +60,6 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch) {
 //   l[i] += u_k log2(f_k/fc_i) (k owned by i)
 // where u_k = dL/dH_k * H_k.
 // Then (thread 0) the chain rule through the anchors gives dL/dfc, dL/dA.
-__device__ __forceinline__ void finish_param_grads(const FilterSegs& sg, const float* f, int F,
-                                                   const double* s, const double* l,
-                                                   double* gfc, double* gA) {
-  const double alpha = 0.11512925464970229;   // ln(10)/20
-  const double ln2 = 0.6931471805599453;
-  for (int i = 0; i < sg.K; ++i) { gfc[i] = 0.0; gA[i] = 0.0; }
-  for (int i = 0; i < sg.K; ++i) {
-    if (sg.kf[i] >= F) continue;                 // owns no bin, s[i] = l[i] = 0
-    gA[i] += alpha * l[i];
-    gfc[i] += -alpha * (double)sg.A[i] / ((double)sg.fc[i] * ln2) * s[i];
-    int c = i;
-    while (sg.parent[c] >= 0) {
-      const int j = sg.parent[c];
-      gA[j] += alpha * (double)log2f(__fdiv_rn(f[sg.kf[c]], sg.fc[j])) * s[i];
-      gfc[j] += -alpha * (double)sg.A[j] / ((double)sg.fc[j] * ln2) * s[i];
-      c = j;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(FIT_THREADS, 1)
 k_design_filter_vjp(const float* fc, const float* A, int K, const float* gain_db,
                     const float* freqs, int F, const float* gH, float* gfc_out, float* gA_out,

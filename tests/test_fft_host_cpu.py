@@ -69,16 +69,22 @@ def test_filter_design_device_logic_on_host(tmp_path, golden):
            "-I", os.path.join(ROOT, "include")]
     subprocess.run(cmd, check=True, capture_output=True, timeout=600)
 
-    def run(f, fc, A):
+    def run(f, fc, A, gH=None):
         fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
         with open(fin, "wb") as fh:
             np.asarray([f.size, fc.size], dtype=np.int32).tofile(fh)
             f.astype(np.float32).tofile(fh)
             fc.astype(np.float32).tofile(fh)
             A.astype(np.float32).tofile(fh)
+            if gH is not None:
+                gH.astype(np.float32).tofile(fh)
         subprocess.run([exe, fin, fout], check=True, timeout=60)
         raw = np.fromfile(fout, dtype=np.float32)
-        return raw[:f.size], int(raw[f.size:].view(np.int32)[0])
+        H, bad = raw[:f.size], int(raw[f.size:f.size + 1].view(np.int32)[0])
+        if gH is None:
+            return H, bad
+        K = fc.size
+        return H, bad, raw[f.size + 1:f.size + 1 + K], raw[f.size + 1 + K:f.size + 1 + 2 * K]
 
     for tag in ("operator_n1024.npz", "operator_n4096.npz"):
         g = golden(tag)
@@ -89,6 +95,11 @@ def test_filter_design_device_logic_on_host(tmp_path, golden):
         assert bad == 0 and np.linalg.norm(H - g["H_dup"]) / np.linalg.norm(g["H_dup"]) < 2e-6
         H, bad = run(f, np.asarray([1000.0]), np.asarray([-20.0]))
         assert np.linalg.norm(H - g["H_list"]) / np.linalg.norm(g["H_list"]) < 2e-6
+        # analytic gradients wrt (fc, A) through the anchor chain against the reference's autograd
+        for cot, kfc, kA, tol in (("cotH", "gfc", "gA", 2e-5), ("fit_gH", "fit_gfc", "fit_gA", 1e-4)):
+            _, _, gfc, gA = run(f, g["fc"], g["A"], g[cot])
+            assert np.linalg.norm(gfc - g[kfc]) / np.linalg.norm(g[kfc]) < tol
+            assert np.linalg.norm(gA - g[kA]) / np.linalg.norm(g[kA]) < tol
     # a breakpoint above the last bin: flagged (the reference raises IndexError there)
     _, bad = run(g["f"], np.asarray([500.0, 1e6]), np.asarray([-10.0, -20.0]))
     assert bad == 1
