@@ -40,6 +40,15 @@ BABE_HD float rn_mul(float a, float b) {
 #endif
 }
 
+BABE_HD float rn_sub(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fsub_rn(a, b);
+#else
+  volatile float q = a - b;
+  return q;
+#endif
+}
+
 BABE_HD float seg_gain(float A, float fc, float f) {
   // 10 ** (A * log2(f / fc) / 20)
   const float t = rn_div(rn_mul(A, log2f(rn_div(f, fc))), 20.0f);
@@ -148,6 +157,39 @@ BABE_HD void finish_param_grads(const FilterSegs& sg, const float* f, int F,
       c = j;
     }
   }
+}
+
+// Projection step of the filter fit (testing/blind_bwe_sampler.py:576-583): SEQUENTIAL clamps -- every
+// breakpoint at least 1 Hz above its predecessor, every slope at most its predecessor's (or Amax).
+BABE_HD void fit_project(float* fc, float* A, int K, const babe_fit_config& cfg) {
+  if (cfg.clamp_fc) {
+    fc[0] = fminf(fmaxf(fc[0], cfg.fcmin), cfg.fcmax);
+    for (int k = 1; k < K; ++k)
+#ifdef __CUDA_ARCH__
+      fc[k] = fminf(fmaxf(fc[k], __fadd_rn(fc[k - 1], 1.0f)), cfg.fcmax);
+#else
+      fc[k] = fminf(fmaxf(fc[k], fc[k - 1] + 1.0f), cfg.fcmax);
+#endif
+  }
+  if (cfg.clamp_A) {
+    const float top0 = cfg.only_negative_A ? -1.0f : cfg.Amax;
+    A[0] = fminf(fmaxf(A[0], cfg.Amin), top0);
+    for (int k = 1; k < K; ++k) {
+      const float top = cfg.only_negative_A ? A[k - 1] : cfg.Amax;
+      A[k] = fminf(fmaxf(A[k], cfg.Amin), top);
+    }
+  }
+}
+
+// Stopping test (:586-588): mean absolute change of fc and of A below their tolerances.
+BABE_HD bool fit_converged(const float* fc, const float* A, const float* fc_prev, const float* A_prev, int K,
+                           const babe_fit_config& cfg) {
+  float d0 = 0.f, d1 = 0.f;
+  for (int k = 0; k < K; ++k) {
+    d0 += fabsf(fc[k] - fc_prev[k]);
+    d1 += fabsf(A[k] - A_prev[k]);
+  }
+  return d0 / (float)K < cfg.tol_fc && d1 / (float)K < cfg.tol_A;
 }
 
 }  // namespace babe

@@ -220,27 +220,8 @@ __global__ void __launch_bounds__(FIT_THREADS, 1) k_fit_params(const FitArgs a) 
       }
       __syncwarp();
       if (lane == 0) {                                                  // sequential clamps (:576-583)
-        if (a.cfg.clamp_fc) {
-          cur[0] = fminf(fmaxf(cur[0], a.cfg.fcmin), a.cfg.fcmax);
-          for (int k = 1; k < K; ++k)
-            cur[k] = fminf(fmaxf(cur[k], __fadd_rn(cur[k - 1], 1.0f)), a.cfg.fcmax);
-        }
-        if (a.cfg.clamp_A) {
-          const float top0 = a.cfg.only_negative_A ? -1.0f : a.cfg.Amax;
-          cur[KMAX] = fminf(fmaxf(cur[KMAX], a.cfg.Amin), top0);
-          for (int k = 1; k < K; ++k) {
-            const float top = a.cfg.only_negative_A ? cur[KMAX + k - 1] : a.cfg.Amax;
-            cur[KMAX + k] = fminf(fmaxf(cur[KMAX + k], a.cfg.Amin), top);
-          }
-        }
-        if (iter > 0) {
-          float d0 = 0.f, d1 = 0.f;
-          for (int k = 0; k < K; ++k) {
-            d0 += fabsf(cur[k] - prev[k]);
-            d1 += fabsf(cur[KMAX + k] - prev[KMAX + k]);
-          }
-          if (d0 / (float)K < a.cfg.tol_fc && d1 / (float)K < a.cfg.tol_A) stop_flag = 1;
-        }
+        fit_project(cur, cur + KMAX, K, a.cfg);
+        if (iter > 0 && fit_converged(cur, cur + KMAX, prev, prev + KMAX, K, a.cfg)) stop_flag = 1;
         for (int k = 0; k < K; ++k) { prev[k] = cur[k]; prev[KMAX + k] = cur[KMAX + k]; }
       }
       __syncwarp();

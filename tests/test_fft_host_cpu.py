@@ -103,3 +103,52 @@ def test_filter_design_device_logic_on_host(tmp_path, golden):
     # a breakpoint above the last bin: flagged (the reference raises IndexError there)
     _, bad = run(g["f"], np.asarray([500.0, 1e6]), np.asarray([-10.0, -20.0]))
     assert bad == 1
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_fit_iteration_device_math_on_host(tmp_path, golden):
+    """The projected-gradient iteration of k_fit_params assembled on the host from the device functions
+    (segments, per-bin gain, chain rule, fp32 step, sequential clamps, stopping test) against the
+    trajectories of the reference's own BlindSampler.fit_params (tests/golden/fit_sampler.npz): 1 and 5
+    iterations tight, 100 iterations loose (the descent is chaotic in fp32)."""
+    import ctypes
+
+    import numpy as np
+    import torch
+    from babe_b200._lib import FitConfig
+    from oracle import stft_filter as osf
+    exe = str(tmp_path / "fit_host_check")
+    src = os.path.join(ROOT, "tests", "host", "fit_host_check.cu")
+    cmd = [NVCC, "-O1", "-std=c++17", "-o", exe, src, "-I", os.path.join(ROOT, "babe_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include")]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+    g = golden("fit_sampler.npz")
+    nfft, sr = int(g["nfft"]), int(g["sr"])
+    F = nfft // 2 + 1
+    a, b, c = osf.stft_mag_stats(torch.from_numpy(g["fit_xden"]).double(), torch.from_numpy(g["y"]).double(), nfft)
+    abc = torch.stack((a, b, c)).numpy().astype(np.float64)
+    w = osf.freq_weight_vector("sqrt", F).numpy().astype(np.float32)
+    f = np.fft.rfftfreq(nfft, d=1 / sr).astype(np.float32)
+
+    def run(p0, iters):
+        cfg = FitConfig(mu_fc=1000, mu_A=10, fcmin=20, fcmax=sr // 2, Amin=-50, Amax=30, tol_fc=5e-3, tol_A=5e-3,
+                        max_iter=iters, clamp_fc=1, clamp_A=1, only_negative_A=1)
+        fin, fout = str(tmp_path / "fit_in.bin"), str(tmp_path / "fit_out.bin")
+        K = p0.shape[1]
+        with open(fin, "wb") as fh:
+            np.asarray([F, K], dtype=np.int32).tofile(fh)
+            fh.write(bytes(cfg))
+            abc.tofile(fh)
+            w.tofile(fh)
+            f.tofile(fh)
+            p0.astype(np.float32).tofile(fh)
+        subprocess.run([exe, fin, fout], check=True, timeout=120)
+        raw = np.fromfile(fout, dtype=np.float32)
+        return raw[:2 * K].reshape(2, K), int(raw[2 * K:].view(np.int32)[0])
+
+    rel = lambda x, y: np.linalg.norm(x - y) / np.linalg.norm(y)
+    for iters, tol in ((1, 1e-5), (5, 1e-5), (100, 3e-2)):
+        p, _ = run(g["fit_p0"], iters)
+        assert rel(p, g[f"fit_p_{iters}"]) < tol, iters
+    p7, _ = run(g["fit7_p0"], 100)
+    assert rel(p7, g["fit7_p"]) < 3e-2
