@@ -574,6 +574,9 @@ def main():
                     help="profiling aid: skip the second (per-kernel event timing) pass")
     ap.add_argument("--no-autotune", action="store_true", help="profiling aid: cudnn.benchmark off")
     a = ap.parse_args()
+    a.steps = max(1, a.steps)
+    if a.impl != "reference":
+        a.warmup = max(1, a.warmup)          # the timed region starts after a completed (untimed) step
     if a.impl == "reference":
         return run_reference(a)
     if a.mode == "operator":
