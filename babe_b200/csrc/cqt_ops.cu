@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "bandfft.cuh"
 #include "smemfft.cuh"
+#include "rfft_pairs.cuh"
 
 namespace babe {
 
@@ -115,28 +116,6 @@ __global__ void __launch_bounds__(CQT_THREADS, 3) k_fft_rows(const PassArgs a) {
 // ---------------------------------------------------------------------------
 // r2c post-processing / c2r pre-processing on bin pairs (k, Nc-k)
 // ---------------------------------------------------------------------------
-// Z = FFT_Nc(x_even + i x_odd)  ->  X[k], X[Nc-k]   (0 < k <= Nc/2)
-__device__ __forceinline__ void post_pair(float2 zk, float2 zkp, float2 W, float2& Xk, float2& Xkp) {
-  const float2 a = zk, b = cconj(zkp);
-  const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
-  const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
-  const float2 O = make_float2(D.y, -D.x);          // -i D
-  const float2 T = cmul(W, O);
-  Xk = make_float2(E.x + T.x, E.y + T.y);
-  Xkp = make_float2(E.x - T.x, -(E.y - T.y));
-}
-// X[k], X[Nc-k] (Hermitian half spectrum)  ->  conj(Z[k])/Nc, conj(Z[Nc-k])/Nc
-__device__ __forceinline__ void pre_pair(float2 Xk, float2 Xkp, float2 W, float inv_nc,
-                                         float2& Zk, float2& Zkp) {
-  const float2 a = Xk, b = cconj(Xkp);
-  const float2 E = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y + b.y));
-  const float2 D = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y - b.y));
-  const float2 O = cmul(cconj(W), D);
-  // Z[k] = E + i O ; Z[kp] = conj(E) + i conj(O); stored conjugated and scaled
-  Zk = make_float2((E.x - O.y) * inv_nc, -(E.y + O.x) * inv_nc);
-  Zkp = make_float2((E.x + O.y) * inv_nc, -(-E.y + O.x) * inv_nc);
-}
-
 __global__ void k_rfft_post(const float2* Z, float2* X, int Nc, const float2* tw_ls,
                             const float* scale) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -152,3 +152,16 @@ def test_fit_iteration_device_math_on_host(tmp_path, golden):
         assert rel(p, g[f"fit_p_{iters}"]) < tol, iters
     p7, _ = run(g["fit7_p0"], 100)
     assert rel(p7, g["fit7_p"]) < 3e-2
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_rfft_pair_processing_on_host(tmp_path):
+    """csrc/rfft_pairs.cuh: real FFT of Ls points from the complex FFT of Ls/2 points and back."""
+    exe = str(tmp_path / "rfft_pairs_host_check")
+    src = os.path.join(ROOT, "tests", "host", "rfft_pairs_host_check.cu")
+    cmd = [NVCC, "-O1", "-std=c++17", "-o", exe, src, "-I", os.path.join(ROOT, "babe_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include")]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout
+    vals = dict(l.split() for l in out.strip().splitlines())
+    assert float(vals["post"]) < 5e-7 and float(vals["pre"]) < 5e-7
