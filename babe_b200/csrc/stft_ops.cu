@@ -31,6 +31,7 @@
 #include "regfft.cuh"
 #include "regfft_packed.cuh"
 #include "stft_cores.cuh"
+#include "stft_fused.cuh"
 
 namespace babe {
 
@@ -827,13 +828,26 @@ extern "C" int babe_apply_filter(const float* x, float* y, int B, int T, int nff
   a.sub = adjoint ? nullptr : sub; a.row_scale = row_scale; a.row_sumsq = row_sumsq;
   a.status = status;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nfft == 4096 && fused_filter_eligible(x, a.sub, T)) {
+    // second-generation kernel: TMA-staged frame tiles, Core4k transform (stft_fused.cu)
+    FusedArgs f{};
+    f.x = x; f.y = y; f.B = B; f.T = T; f.window = window; f.roots = a.twiddle;
+    f.H = H; f.freqs = freqs; f.fc = fc; f.A = A; f.K = K; f.adjoint = adjoint;
+    f.sub = a.sub; f.row_scale = row_scale; f.status = status;
+    if (row_sumsq != nullptr) {
+      BABE_REQUIRE(workspace != nullptr && workspace_bytes >= fused_sumsq_slots(B, T) * sizeof(double), BABE_EBADARG,
+                   "apply_filter: row_sumsq needs a workspace of babe_apply_filter_workspace() bytes");
+      f.item_sumsq = static_cast<double*>(workspace);
+    }
+    return launch_filter_fused(f, row_sumsq, st);
+  }
   BABE_DISPATCH_NFFT(nfft, return (launch_apply_filter<G, GR>(a, workspace, workspace_bytes, st)));
   return BABE_EUNSUPPORTED;
 }
 
 extern "C" size_t babe_apply_filter_workspace(int B, int T, int nfft) {
   if (!babe_stft_supported(nfft) || B < 1 || T < 1) return 0;
-  return (size_t)B * ((T - 1) / (nfft / 2) + 1) * sizeof(double);
+  return (size_t)B * ((T - 1) / (nfft / 2) + 2) * sizeof(double);   // >= one partial per (CTA, row) segment
 }
 
 extern "C" size_t babe_stft_stats_workspace(int B, int T, int nfft) {
@@ -855,6 +869,21 @@ extern "C" int babe_stft_stats(const float* x, const float* y, int B, int T, int
   a.x = x; a.y = y; a.B = B; a.T = T; a.window = window;
   a.twiddle = reinterpret_cast<const float2*>(twiddle); a.mode = mode;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nfft == 4096 && fused_stats_eligible(x, y, T, mode)) {
+    // second-generation kernel: TMA-staged frames, Core4k transform, register accumulators (stft_fused.cu)
+    FusedStatsArgs f{};
+    f.x = x; f.y = y; f.B = B; f.T = T; f.window = window; f.roots = a.twiddle;
+    const size_t need = (size_t)2 * sm_count() * 3 * Core3::F * sizeof(float);
+    BABE_REQUIRE(workspace != nullptr && workspace_bytes >= need, BABE_EBADARG,
+                 "stft_stats: workspace too small (%zu < %zu)", workspace_bytes, need);
+    f.partial = static_cast<float*>(workspace);
+    int n_partials = 0;
+    int rc = launch_stats_fused(f, &n_partials, st);
+    if (rc) return rc;
+    const int n = 3 * Core3::F;
+    k_reduce_stats<<<(n + 31) / 32, 256, 0, st>>>(f.partial, n_partials, n, abc);
+    return check_launch("k_reduce_stats");
+  }
   switch (nfft) {
     case 4096: return launch_stats<Core3, 1>(a, abc, workspace, workspace_bytes, st);
     case 2048: return launch_stats<Core2<32, 64>, 4>(a, abc, workspace, workspace_bytes, st);

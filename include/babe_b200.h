@@ -64,6 +64,16 @@ int babe_design_filter_vjp(const float* fc, const float* A, int K, const float* 
                            const float* freqs, int F, const float* gH,
                            float* gfc, float* gA, float* ggain, void* stream);
 
+/* ---- kernel selection (profiling / A-B measurements; not needed for normal use) ----------- */
+/* Which implementation serves NFFT = 4096 in babe_apply_filter / babe_stft_stats / babe_fir_filter:
+ *    0 (default)  second-generation kernels (csrc/stft_fused.cu): frame tiles staged by 1-D bulk TMA copies
+ *                 (cp.async.bulk + mbarrier), the batch cut into equal contiguous runs of output blocks;
+ *   -1            the round-1 kernels (cp.async staging), which also serve rows that cannot be bulk-copied
+ *                 (length not a multiple of 4 samples, misaligned base).
+ * Process-wide, not thread-safe against concurrent launches. */
+int babe_set_fused_variant(int variant);
+int babe_get_fused_variant(void);
+
 /* ---- a3/a12: fused STFT -> H -> iSTFT ---------------------------------- */
 /* Replaces apply_filter (utils/blind_bwe_utils.py:6-13) and
  * BlindSampler.apply_filter_fcA (testing/blind_bwe_sampler.py:518-520).
