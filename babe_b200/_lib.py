@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbabe_b200.so")
+LIB_PATH = os.environ.get("BABE_B200_LIB") or os.path.join(_HERE, "libbabe_b200.so")
 
 BABE_OK, BABE_EBADARG, BABE_EUNSUPPORTED, BABE_ECUDA = 0, -1, -2, -3
 MAX_BREAKPOINTS = 16

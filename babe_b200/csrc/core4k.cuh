@@ -43,12 +43,18 @@ struct Core4k {
   };
 
   // ---- forward -----------------------------------------------------------------------------------
-  template <class TW>
-  BABE_HD static void fwd_p1(float2 (&z)[16], float2* ex, const TW& tw, int t) {
-    fft16v<false>(z);
+  // SCALED: the transform of z[n1] * s[n1] (the analysis window rides on the first butterflies)
+  template <class TW, bool SCALED = false>
+  BABE_HD static void fwd_p1(float2 (&z)[16], float2* ex, const TW& tw, int t, const float (&s)[16]) {
+    fft16v_impl<false, SCALED>(z, s);
     ex[t] = z[0];
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) ex[k1 * PITCH + t] = c_mul(z[k1], tw.get(k1));
+  }
+  template <class TW>
+  BABE_HD static void fwd_p1(float2 (&z)[16], float2* ex, const TW& tw, int t) {
+    const float none[16] = {};
+    fwd_p1<TW, false>(z, ex, tw, t, none);
   }
   BABE_HD static void fwd_p2_load(float2 (&v)[16], const float2* ex, int t) {
     const float2* row = ex + (t >> 4) * PITCH + (t & 15);
@@ -70,13 +76,19 @@ struct Core4k {
     fft16v<false>(v);
   }
   // ---- inverse (unnormalised) -----------------------------------------------------------------------
-  BABE_HD static void inv_q1(float2 (&v)[16], float2* ex, const float2* tw3, int t) {
-    fft16v<true>(v);
+  // SCALED: the inverse transform of v[k3] * s[k3] (the filter gain rides on the first butterflies)
+  template <bool SCALED = false>
+  BABE_HD static void inv_q1(float2 (&v)[16], float2* ex, const float2* tw3, int t, const float (&s)[16]) {
+    fft16v_impl<true, SCALED>(v, s);
     float2* row = ex + (t >> 4) * PITCH + 17 * (t & 15);
     const float2* w = tw3 + (t & 15);
     row[0] = v[0];
 #pragma unroll
     for (int n3 = 1; n3 < 16; ++n3) row[n3] = c_mulc(v[n3], w[16 * n3]);
+  }
+  BABE_HD static void inv_q1(float2 (&v)[16], float2* ex, const float2* tw3, int t) {
+    const float none[16] = {};
+    inv_q1<false>(v, ex, tw3, t, none);
   }
   BABE_HD static void inv_q2_load(float2 (&v)[16], const float2* ex, int t) {
     const float2* row = ex + (t >> 4) * PITCH + (t & 15);

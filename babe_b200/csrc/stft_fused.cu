@@ -195,12 +195,14 @@ __global__ void __launch_bounds__(256, 2) k_filter_fused(const FusedArgs a) {
           }
         }
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-          const float w = n1 < 8 ? wa_lo[256 * n1] : wa_hi[256 * (15 - n1)];
-          z[n1] = c_scale(make_float2(xs[n1], xs[n1 + 8]), w);
-        }
+        for (int n1 = 0; n1 < 16; ++n1) z[n1] = make_float2(xs[n1], xs[n1 + 8]);
       }
-      C::fwd_p1(z, ex, tw, t);
+      {
+        float w[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) w[n1] = n1 < 8 ? wa_lo[256 * n1] : wa_hi[256 * (15 - n1)];
+        C::fwd_p1<C::TwRegs, true>(z, ex, tw, t, w);
+      }
       group_sync<256>(1);
       if (t == 0 && fA + 2 <= fe)                                // every thread has read the stage
         issue_copy(stage, mbar, xr, a.T, (long long)(fA + 2) * C::HOP, 3 * C::HOP);
@@ -209,9 +211,12 @@ __global__ void __launch_bounds__(256, 2) k_filter_fused(const FusedArgs a) {
       C::fwd_p2_store(z, ex, t);
       __syncwarp();
       C::fwd_p3(z, ex, tw3, t);
+      {
+        float h[16];
 #pragma unroll
-      for (int k3 = 0; k3 < 16; ++k3) z[k3] = c_scale(z[k3], k3 < 8 ? hp_lo[256 * k3] : hp_hi[256 * (15 - k3)]);
-      C::inv_q1(z, ex, tw3, t);            // writes exactly the 16 entries this thread read in fwd_p3
+        for (int k3 = 0; k3 < 16; ++k3) h[k3] = k3 < 8 ? hp_lo[256 * k3] : hp_hi[256 * (15 - k3)];
+        C::inv_q1<true>(z, ex, tw3, t, h);   // writes exactly the 16 entries this thread read in fwd_p3
+      }
       __syncwarp();
       C::inv_q2_load(z, ex, t);
       __syncwarp();
@@ -376,10 +381,13 @@ __global__ void __launch_bounds__(256, 2) k_stats_fused(const FusedStatsArgs a) 
           z[n1] = make_float2(in ? stage[256 * n1 + t] : 0.f, in ? stage[C::N + 256 * n1 + t] : 0.f);
         }
       }
-#pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) z[n1] = c_scale(z[n1], n1 < 8 ? w_lo[256 * n1] : w_hi[256 * (15 - n1)]);
     }
-    C::fwd_p1(z, ex, tw, t);
+    {
+      float w[16];
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) w[n1] = n1 < 8 ? w_lo[256 * n1] : w_hi[256 * (15 - n1)];
+      C::fwd_p1<C::TwRegs, true>(z, ex, tw, t, w);
+    }
     group_sync<256>(1);
     if (t == 0 && g + 1 < g1) issue(g + 1);          // every thread has read the stage
     C::fwd_p2_load(z, ex, t);

@@ -9,9 +9,13 @@ constexpr int ITERS = 4096;
 
 template <int KIND, int ILP>
 __global__ void k(float2* out, long long* cyc, float2 s, float2 c) {
-  float2 v[ILP];
+  float2 v[ILP], u[ILP], w[ILP];
 #pragma unroll
-  for (int i = 0; i < ILP; ++i) v[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+  for (int i = 0; i < ILP; ++i) {
+    v[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+    u[i] = make_float2(1.0f + 1e-6f * (i + threadIdx.x), 1.0f - 1e-6f * i * s.x);
+    w[i] = make_float2(1e-3f * i * c.x, 1e-3f * (i + 1) * c.y);
+  }
   __syncthreads();
   const long long t0 = clock64();
   for (int it = 0; it < ITERS; ++it) {
@@ -25,6 +29,15 @@ __global__ void k(float2* out, long long* cyc, float2 s, float2 c) {
       if (KIND == 5) { v[i].x = fmaf(v[i].x, s.x, c.x); v[i].y = fmaf(v[i].y, s.y, c.y); }  // 2 x FFMA
       if (KIND == 6) { v[i].x = v[i].x * s.x; }                                             // FMUL
       if (KIND == 7) { v[i].x = fmaf(v[i].x, 1.0001f, 0.5f); }                              // FFMA imm
+      if (KIND == 8) { v[i] = __ffma2_rn(v[i], u[i], w[i]); }                               // FFMA2, 3 distinct register pairs
+      if (KIND == 9) { if (i & 1) v[i] = __ffma2_rn(v[i], s, c); else v[i].x = fmaf(v[i].x, s.x, c.x); }   // FFMA2 + FFMA alternating
+      if (KIND == 10) { if (i & 1) v[i] = __fadd2_rn(v[i], c); else v[i].x = fmaf(v[i].x, s.x, c.x); }     // FADD2 + FFMA alternating
+      if (KIND == 13) { if ((i & 3) == 0) v[i] = __ffma2_rn(v[i], s, c); else v[i].x = fmaf(v[i].x, s.x, c.x); }   // 1 FFMA2 : 3 FFMA
+      if (KIND == 14) { if ((i & 3) < 2) v[i] = __ffma2_rn(v[i], s, c); else v[i].x = fmaf(v[i].x, s.x, c.x); }    // 2 FFMA2 : 2 FFMA (grouped)
+      if (KIND == 15) { if ((i & 7) == 0) v[i] = __ffma2_rn(v[i], s, c); else v[i].x = fmaf(v[i].x, s.x, c.x); }   // 1 FFMA2 : 7 FFMA
+      if (KIND == 16) { if (i & 1) v[i] = __ffma2_rn(v[i], s, c); else v[i].x = v[i].x * s.x; }   // FFMA2 + FMUL alternating
+      if (KIND == 11) { v[i].x = fmaf(v[i].x, u[i].x, w[i].x); }                            // FFMA, 3 distinct registers
+      if (KIND == 12) { v[i] = __fadd2_rn(v[i], w[i]); }                                    // FADD2, 2 distinct pairs
     }
   }
   const long long t1 = clock64();
@@ -67,6 +80,17 @@ int main() {
     run<4, 8>("FMUL2", threads, 1, 1);
     run<5, 8>("2xFFMA", threads, 1, 2);
   }
+  run<8, 8>("FFMA2.3r", 512, 1, 1);
+  run<11, 8>("FFMA.3r", 512, 1, 1);
+  run<12, 8>("FADD2.2r", 512, 1, 1);
+  run<9, 8>("FFMA2+FFMA", 512, 1, 1);
+  run<10, 8>("FADD2+FFMA", 512, 1, 1);
+  run<13, 8>("1xFFMA2:3xFFMA", 512, 1, 1);
+  run<14, 8>("2xFFMA2:2xFFMA", 512, 1, 1);
+  run<15, 8>("1xFFMA2:7xFFMA", 512, 1, 1);
+  run<16, 8>("FFMA2+FMUL", 512, 1, 1);
+  run<9, 8>("FFMA2+FFMA", 256, 1, 1);
+  run<9, 8>("FFMA2+FFMA", 1024, 1, 1);
   run<0, 4>("FFMA", 512, 1, 1);
   run<2, 4>("FFMA2", 512, 1, 1);
   run<0, 16>("FFMA", 512, 1, 1);

@@ -102,6 +102,15 @@ int main() {
       den += fr * fr + fi * fi + ir * ir + ii * ii;
     }
     printf("fft16 %.3e\n", sqrt(num / den));
+    // scaled first stage == transform of the pre-scaled values
+    float sc[16];
+    float2 c[16], d[16];
+    double n2 = 0, d2 = 0;
+    for (int i = 0; i < 16; ++i) { sc[i] = 0.5f + rnd(); c[i] = v[i]; d[i] = make_float2(v[i].x * sc[i], v[i].y * sc[i]); }
+    fft16v_scaled<true>(c, sc);
+    fft16v<true>(d);
+    for (int i = 0; i < 16; ++i) { n2 += (c[i].x - d[i].x) * (c[i].x - d[i].x) + (c[i].y - d[i].y) * (c[i].y - d[i].y); d2 += d[i].x * d[i].x + d[i].y * d[i].y; }
+    printf("fft16_scaled %.3e\n", sqrt(n2 / d2));
   }
   run<Core4k::TwRegs>(roots, tw4, false);
   run<Core4k::TwSmem>(roots, tw4, true);

@@ -165,3 +165,22 @@ def test_rfft_pair_processing_on_host(tmp_path):
     out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout
     vals = dict(l.split() for l in out.strip().splitlines())
     assert float(vals["post"]) < 5e-7 and float(vals["pre"]) < 5e-7
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_core4k_passes_on_host(tmp_path):
+    """Core4k (csrc/core4k.cuh) and fft16v (csrc/fft16v.cuh): the 4096-point core of the round-2 fused kernels
+    (csrc/stft_fused.cu) -- forward / inverse passes with the half-warp-local second exchange, both twiddle
+    sources, the scaled first butterfly stage and the permuted real-symmetric table addressing -- emulated
+    thread by thread on the host against naive double-precision DFTs."""
+    exe = str(tmp_path / "core4k_host_check")
+    src = os.path.join(ROOT, "tests", "host", "core4k_host_check.cu")
+    cmd = [NVCC, "-O1", "-std=c++17", "-o", exe, src, "-I", os.path.join(ROOT, "babe_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include")]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout
+    vals = dict(l.split() for l in out.strip().splitlines())
+    assert float(vals["fft16"]) < 2e-7 and float(vals["fft16_scaled"]) < 3e-7
+    for k in ("fwd_regs", "fwd_smem", "roundtrip_regs", "roundtrip_smem"):
+        assert float(vals[k]) < 5e-7, (k, vals[k])
+    assert float(vals["perm"]) == 0.0
