@@ -200,7 +200,7 @@ class _Plan:
         buf = self._ws.get(rows)
         if buf is None or buf.numel() * 4 < n:
             buf = torch.empty((n + 3) // 4, dtype=torch.float32, device=self.device)
-            self._ws = {rows: buf}
+            self._ws[rows] = buf            # never drop a buffer: a captured CUDA graph may hold its address
         return buf, n
 
 

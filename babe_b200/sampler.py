@@ -197,7 +197,30 @@ class BlindSamplerFused:
             return self.noise_fn(shape, device)
         if self.device_noise:
             return torch.randn(shape, device=device, generator=self.generator)
-        return torch.randn(shape).to(device)       # reference: host generator (:513, edm.py:105)
+        if torch.device(device).type != "cuda":
+            return torch.randn(shape).to(device)   # reference: host generator (:513, edm.py:105)
+        return self._host_randn_pinned(tuple(shape), device)
+
+    def _host_randn_pinned(self, shape, device):
+        """The reference's ``torch.randn(shape).to(device)`` -- same host generator stream, same values --
+        drawn into one of two page-locked staging buffers and copied asynchronously (a pageable source makes
+        the copy synchronous and ~2x slower)."""
+        ring = self.__dict__.setdefault("_noise_ring", {})
+        slot = ring.get(shape)
+        if slot is None:
+            slot = ring[shape] = {"bufs": [torch.empty(shape, pin_memory=True) for _ in range(2)],
+                                  "events": [None, None], "i": 0}
+        i = slot["i"]
+        slot["i"] = 1 - i
+        if slot["events"][i] is not None:
+            slot["events"][i].synchronize()        # the previous copy out of this buffer has completed
+        buf = slot["bufs"][i]
+        torch.randn(shape, out=buf)
+        out = buf.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot["events"][i] = ev
+        return out
 
     def move_timestep(self, x, t, gamma, Snoise=1):
         """testing/blind_bwe_sampler.py:509-516 (always draws)."""
@@ -345,10 +368,12 @@ class BlindSamplerFused:
         return norms, grads
 
     # -- the sampling loop ---------------------------------------------------
-    def predict_blind_bwe(self, y, rid=False, compute_sweep=False, max_steps=None, step_hook=None):
+    def predict_blind_bwe(self, y, rid=False, compute_sweep=False, max_steps=None, step_hook=None,
+                          start_step=0, init_x=None, init_params=None):
         """testing/blind_bwe_sampler.py:619-769.  ``max_steps`` bounds the loop
         (benchmarks); ``step_hook(i, x, filter_params)`` is called after each
-        step."""
+        step.  ``start_step`` / ``init_x`` / ``init_params`` resume the loop from a given state
+        (teacher-forced parity tests: one step from each state of a reference run)."""
         args = self.args
         device = y.device
         self.freqs = torch.fft.rfftfreq(args.tester.blind_bwe.NFFT, d=1 / args.exp.sample_rate).to(device)
@@ -359,6 +384,8 @@ class BlindSamplerFused:
                                       args.tester.blind_bwe.initial_conditions.A]).to(device)
         if len(filter_params.shape) == 1:
             filter_params.unsqueeze_(1)
+        if init_params is not None:
+            filter_params = init_params.to(device).clone()
         if compute_sweep:
             self.fc_s = torch.logspace(2.5, 4, 15).to(device)
             self.A_s = torch.linspace(-80, -5, 12).to(device)
@@ -371,15 +398,15 @@ class BlindSamplerFused:
 
         if self.start_sigma is None:
             t = self.diff_params.create_schedule(self.nb_steps).to(device)
-            x = self._randn(shape, device) * t[0]
+            x = self._randn(shape, device) * t[0] if init_x is None else init_x.to(device)
         else:
             t = self.diff_params.create_schedule_from_initial_t(self.start_sigma, self.nb_steps).to(device)
-            x = y + self._randn(shape, device) * t[0]
+            x = y + self._randn(shape, device) * t[0] if init_x is None else init_x.to(device)
         gamma = self.diff_params.get_gamma(t).to(device)
         t_host = t.cpu()
-        n_steps = self.nb_steps if max_steps is None else min(max_steps, self.nb_steps)
+        n_steps = self.nb_steps if max_steps is None else min(start_step + max_steps, self.nb_steps)
 
-        for i in range(n_steps):
+        for i in range(start_step, n_steps):
             x_hat, t_hat = self.move_timestep(x, t[i], gamma[i])
             score, filter_params, x_den_2 = self._evaluate(x_hat, t_hat, y, filter_params)
             if compute_sweep:

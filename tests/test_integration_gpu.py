@@ -1,0 +1,97 @@
+"""GPU: integration row of SURVEY section 4 against the golden produced by the UNMODIFIED reference sampler driving the
+UNMODIFIED reference network (tests/golden/make_golden_integration.py; the network on the oracle CQT).
+
+* the CUDA ``CQT_nsgt`` + ``CQTDiffPlus`` reproduce one evaluation of the reference network;
+* parity mode: ``babe_b200.install()`` routes ``utils.blind_bwe_utils`` to the CUDA drop-ins and the reference's own
+  call pattern (tests/parity_loop.py, validated against the reference on the CPU by tests/test_integration_cpu.py)
+  runs on them, TF32 off, with the reference's noise draws; compared per step;
+* throughput mode: ``BlindSamplerFused`` on the same inputs;
+* the three Hydra callable strings resolve to the CUDA classes and run.
+"""
+import importlib
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+    return torch.from_numpy(np.asarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def world(golden):
+    from babe_b200 import build
+    build.build()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from babe_b200 import callables
+    from babe_b200.sampler import make_args
+    args = make_args(sample_rate=22050, audio_len=4096, num_octs=3, bins_per_oct=8, NFFT=1024, T=2, max_iter=5)
+    args.network.Ns, args.network.Ss, args.network.num_dils = [8, 8, 16], [2, 2, 2], [1, 2, 2]
+    args.network.attention_layers, args.network.emb_dim = [0, 0, 0, 0], 32
+    g = golden("integration.npz")
+    torch.manual_seed(0)
+    net = callables.call_func_by_name(func_name=args.network.callable, args=args, device=torch.device("cuda")).cuda()
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if ".gate." in n and n.endswith("weight"):
+                p.mul_(1e6)
+    for p in net.parameters():
+        p.requires_grad_(False)
+    return args, g, net
+
+
+def test_network_evaluation_matches_reference(world):
+    args, g, net = world
+    out = net(cuda(g["net_in"]), cuda(g["net_sigma"]))
+    assert rel_l2(out.cpu(), g["net_out"]) < 1e-5
+
+
+def test_parity_mode_through_install(world):
+    import babe_b200
+    import parity_loop
+    from babe_b200 import callables
+    args, g, net = world
+    saved = {k: sys.modules.get(k) for k in ("utils", "utils.blind_bwe_utils")}
+    try:
+        babe_b200.install()
+        bu = importlib.import_module("utils.blind_bwe_utils")       # what testing/blind_bwe_sampler.py:9 does
+        assert bu.__name__ == "babe_b200.blind_bwe_utils"
+        diff = callables.call_func_by_name(func_name=args.diff_params.callable, args=args)
+        draws = iter(g["draws"])
+        trace = []
+        x, p = parity_loop.predict_blind_bwe(bu, net, diff, args, cuda(g["y"]).clone(),
+                                             randn=lambda shape: torch.from_numpy(next(draws)), trace=trace)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    for i, (xi, pi, di) in enumerate(trace):
+        assert rel_l2(di.cpu(), g["x_den"][i]) < 2e-5, i
+        assert rel_l2(xi.cpu(), g["x_out"][i]) < 2e-5, i
+    assert rel_l2(p.cpu(), g["params"]) < 1e-4
+    assert rel_l2(x.cpu(), g["x"]) < 2e-5
+
+
+def test_fused_sampler_with_real_network(world):
+    from babe_b200 import callables
+    args, g, net = world
+    diff = callables.call_func_by_name(func_name=args.diff_params.callable, args=args)
+    smp = callables.call_func_by_name(func_name=args.tester.sampler_callable, model=net, diff_params=diff, args=args,
+                                      rid=True)
+    draws = iter(g["draws"])
+    smp.noise_fn = lambda shape, dev: cuda(next(draws))
+    x, p, den, t, filt = smp.predict_blind_bwe(cuda(g["y"]).clone(), rid=True)
+    assert rel_l2(t.cpu(), g["t"]) < 1e-6
+    assert rel_l2(den, g["x_den"]) < 2e-5
+    assert rel_l2(filt, g["filters"]) < 1e-4
+    assert rel_l2(p.cpu(), g["params"]) < 1e-4
+    assert rel_l2(x.cpu(), g["x"]) < 2e-5

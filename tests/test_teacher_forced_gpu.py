@@ -1,0 +1,126 @@
+"""GPU: teacher-forced parity.  The chained comparisons of tests/test_operator_gpu.py::test_fit_params_vs_oracle
+and tests/test_sampler_gpu.py tolerate 1e-3 .. 3e-2 because the projected gradient descent of the filter fit
+(mu = 1000 on fc, bin-anchored H discontinuous in fc) amplifies fp32 rounding -- the reference's own fp32 run drifts
+1.5e-2 from its fp64 evaluation.  Here every single iteration of the fit kernel and every single step of the fused
+sampler is started FROM THE REFERENCE'S OWN ITERATE / STATE (tests/golden/make_golden_tf.py: unmodified
+BlindSampler.fit_params and predict_blind_bwe, testing/blind_bwe_sampler.py:533-595, 619-769) and must land on the
+reference's next iterate / state at the 1e-5 of BASELINE.json's north star."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from toy_model import ToyDenoiser
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def cuda(a):
+    return torch.from_numpy(np.asarray(a)).cuda()
+
+
+@pytest.mark.parametrize("case,inputs,xk,yk,nfft_key", [
+    ("n1024", "fit_sampler.npz", "fit_xden", "y", "nfft"),
+    ("k7", "fit_sampler.npz", "fit_xden", "y", "nfft"),
+    ("n4096", "operator_n4096.npz", "x", "yobs", "nfft"),
+])
+def test_fit_iteration_from_every_reference_iterate(golden, case, inputs, xk, yk, nfft_key):
+    """k_fit_params with max_iter = 1 from each of the reference's 100 iterates == the reference's next iterate."""
+    from babe_b200 import build
+    build.build()
+    from babe_b200 import sampler
+    tf, g = golden("teacher_forced.npz"), golden(inputs)
+    its = tf[f"fit_iters_{case}"]
+    nfft, sr = int(g[nfft_key]), int(g["sr"])
+    xden, y = cuda(g[xk]), cuda(g[yk])
+    fit = sampler.FilterFit(nfft=nfft, sample_rate=sr, max_iter=1, device="cuda")
+    abc = fit.stats(xden, y)
+    worst_fc = worst_A = 0.0
+    for i in range(its.shape[0] - 1):
+        p = fit(xden, y, cuda(its[i]).clone().contiguous(), abc=abc).cpu().numpy()
+        worst_fc = max(worst_fc, rel_l2(p[0], its[i + 1][0]))
+        worst_A = max(worst_A, rel_l2(p[1], its[i + 1][1]))
+    assert worst_fc < TOL and worst_A < TOL, (case, worst_fc, worst_A)
+
+
+def _sampler(tf, max_iter):
+    from babe_b200 import edm, sampler
+    y = cuda(tf["step_y"])
+    args = sampler.make_args(sample_rate=int(tf["step_sr"]), audio_len=y.shape[1], T=4, NFFT=int(tf["step_nfft"]),
+                             max_iter=max_iter)
+    return sampler.BlindSamplerFused(ToyDenoiser().cuda(), edm.EDM(args), args, rid=False), y
+
+
+def test_sampler_step_from_every_reference_state(golden):
+    """ONE step of BlindSamplerFused (stochastic move, denoise, fit, fused guidance, Heun correction with its second
+    fit and guidance) from each state of the reference run, with the reference's own noise draw."""
+    from babe_b200 import build
+    build.build()
+    tf = golden("teacher_forced.npz")
+    s, y = _sampler(tf, int(tf["step_max_iter"]))
+    draws = tf["step_draws"]
+    for i in range(tf["step_x_in"].shape[0]):
+        s.noise_fn = lambda shape, dev, i=i: cuda(draws[i + 1])
+        out = s.predict_blind_bwe(y.clone(), rid=True, max_steps=1, start_step=i, init_x=cuda(tf["step_x_in"][i]),
+                                  init_params=cuda(tf["step_p_in"][i]))
+        x, p, den = out[0], out[1], out[2]
+        assert rel_l2(den[i], tf["step_x_den"][i]) < TOL, i          # denoised estimate of the first evaluation
+        # each step chains 2 x 20 fit iterations: the audio state must stay at 1e-5, the filter parameters are
+        # allowed the amplification measured for 20 chained iterations in the reference's own fp32-vs-fp64 run
+        assert rel_l2(x.cpu(), tf["step_x_out"][i]) < TOL, i
+        assert rel_l2(p.cpu(), tf["step_p_out"][i]) < 2e-4, i
+
+
+def test_sampler_step_with_teacher_forced_fit(golden):
+    """The same with the fit limited to ONE iteration per evaluation from the reference's incoming filter: every
+    quantity of the step -- filter included -- at 1e-5 (the reference's mid-step filter is its 20-iteration result,
+    so the first evaluation's filter is compared after one iteration against teacher_forced fit iterates of the
+    same inputs elsewhere; here the guidance, Heun update and denoiser path are what is pinned)."""
+    from babe_b200 import build
+    build.build()
+    from babe_b200 import sampler as smod
+    tf = golden("teacher_forced.npz")
+    s, y = _sampler(tf, int(tf["step_max_iter"]))
+    draws = tf["step_draws"]
+    i = 1
+    # replace the fit by the reference's own results: the rest of the step must then match at 1e-5 everywhere
+    seq = iter([cuda(tf["step_p_mid"][i]), cuda(tf["step_p_out"][i])])
+    s.fit_params = lambda den, yy, p: next(seq)
+    s.noise_fn = lambda shape, dev: cuda(draws[i + 1])
+    x, p = s.predict_blind_bwe(y.clone(), rid=False, max_steps=1, start_step=i, init_x=cuda(tf["step_x_in"][i]),
+                               init_params=cuda(tf["step_p_in"][i]))
+    assert rel_l2(x.cpu(), tf["step_x_out"][i]) < TOL
+    assert rel_l2(p.cpu(), tf["step_p_out"][i]) == 0.0
+
+
+@pytest.mark.parametrize("variant", ["data_consistency", "smoothl1", "cosine", "stft", "stft_mag", "stft_logmag", "snr"])
+def test_optional_branches_match_reference(golden, variant):
+    """Non-default branches of get_rec_grads / fit_params / the loop (testing/blind_bwe_sampler.py:63-73, 80-86,
+    99-115) against two-step runs of the unmodified reference (same noise draws)."""
+    from babe_b200 import build
+    build.build()
+    from babe_b200 import edm, sampler
+    g = golden("optional_branches.npz")
+    fs = golden("fit_sampler.npz")
+    y = cuda(g[f"opt_{variant}_y"])
+    args = sampler.make_args(sample_rate=int(fs["sr"]), audio_len=y.shape[1], T=2, NFFT=int(fs["nfft"]), max_iter=2)
+    ps = args.tester.posterior_sampling
+    if variant == "data_consistency":
+        ps.data_consistency = True
+    elif variant in ("smoothl1", "cosine"):
+        ps.norm = variant
+    elif variant == "snr":
+        ps.SNR_observations = 30
+    else:
+        ps.stft_distance.use = True
+        ps.stft_distance.nfft = 1024
+        ps.freq_weighting = "sqrt"
+        ps.stft_distance.mag = variant != "stft"
+        ps.stft_distance.logmag = variant == "stft_logmag"
+    s = sampler.BlindSamplerFused(ToyDenoiser().cuda(), edm.EDM(args), args, rid=False)
+    draws = iter(g[f"opt_{variant}_draws"])
+    s.noise_fn = lambda shape, dev: cuda(next(draws))
+    x, p = s.predict_blind_bwe(y.clone())
+    assert rel_l2(p.cpu(), g[f"opt_{variant}_p"]) < 1e-4, variant
+    assert rel_l2(x.cpu(), g[f"opt_{variant}_x"]) < 1e-4, variant
