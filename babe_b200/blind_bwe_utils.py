@@ -123,20 +123,25 @@ class _SpecMagNorm(torch.autograd.Function):
     def forward(ctx, X, Xref, H, w):
         st = ops.spec_mag_stats(X, Xref, H=H, w=w)
         norm64 = torch.sqrt(st[3].sum())
-        ctx.save_for_backward(st, H, w if w is not None else torch.empty(0, device=H.device), norm64)
+        spec = (X, Xref) if (X.requires_grad or Xref.requires_grad) else (torch.empty(0, device=H.device),) * 2
+        ctx.save_for_backward(st, H, w if w is not None else torch.empty(0, device=H.device), norm64, *spec)
         ctx.has_w = w is not None
         return norm64.to(torch.float32)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
+        st, H, w, norm64, X, Xref = ctx.saved_tensors
+        gX = gR = gH = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            raise NotImplementedError("gradient wrt the spectrograms is not implemented; "
-                                      "differentiate through apply_filter instead")
-        st, H, w, norm64 = ctx.saved_tensors
-        w2 = (w.double() ** 2) if ctx.has_w else 1.0
-        gH = g.double() * w2 * (H.double() * st[0] - st[1]) / norm64
-        return None, None, gH.to(torch.float32), None
+            # what autograd gives the reference through sqrt(re^2 + im^2) (utils/blind_bwe_utils.py:254-257)
+            coef = (g.double() / norm64).to(torch.float32)
+            gX, gR = ops.spec_mag_grad(X, Xref, H, w if ctx.has_w else None, coef,
+                                       want_X=ctx.needs_input_grad[0], want_Xref=ctx.needs_input_grad[1])
+        if ctx.needs_input_grad[2]:
+            w2 = (w.double() ** 2) if ctx.has_w else 1.0
+            gH = (g.double() * w2 * (H.double() * st[0] - st[1]) / norm64).to(torch.float32)
+        return gX, gR, gH, None
 
 
 # ---------------------------------------------------------------------------

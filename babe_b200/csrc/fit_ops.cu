@@ -7,6 +7,8 @@
 // eloimoliner/BABE; analytic gradients per SURVEY Appendix A.2 / A.3.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "filter_design.cuh"
 
@@ -293,6 +295,26 @@ __global__ void __launch_bounds__(128) k_spec_mag_stats(const float2* X, const f
   }
 }
 
+// gradient of  norm = || w (H |X| - |Xref|) ||_2  wrt the spectrograms (utils/blind_bwe_utils.py:250-296 under
+// autograd):  dnorm/dX = coef w^2 (H|X| - |Xref|) H X/|X|,   dnorm/dXref = -coef w^2 (H|X| - |Xref|) Xref/|Xref|,
+// coef = upstream gradient / norm (device scalar).  |X| = 0 gives 0/0 = NaN exactly like the reference's sqrt'.
+__global__ void __launch_bounds__(256) k_spec_mag_grad(const float2* X, const float2* Xref, const float* H,
+                                                       const float* w, const float* coef, int F, int frames,
+                                                       long long n, float2* gX, float2* gXref) {
+  const float c = coef[0];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)((i / frames) % F);
+    const float h = H ? H[k] : 1.0f, wk = w ? w[k] : 1.0f;
+    const float2 x = X[i], y = Xref[i];
+    const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+    const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
+    const float d = __fsub_rn(__fmul_rn(__fmul_rn(mx, h), wk), __fmul_rn(my, wk));
+    const float e = c * d * wk;
+    if (gX) { const float s = e * h / mx; gX[i] = make_float2(s * x.x, s * x.y); }
+    if (gXref) { const float s = -e / my; gXref[i] = make_float2(s * y.x, s * y.y); }
+  }
+}
+
 }  // namespace babe
 
 using namespace babe;
@@ -343,4 +365,17 @@ extern "C" int babe_spec_mag_stats(const float* X, const float* Xref, const floa
       reinterpret_cast<const float2*>(X), reinterpret_cast<const float2*>(Xref), H, w, B, F,
       frames, out);
   return check_launch("k_spec_mag_stats");
+}
+
+extern "C" int babe_spec_mag_grad(const float* X, const float* Xref, const float* H, const float* w,
+                                  const float* coef, int B, int F, int frames, float* gX, float* gXref,
+                                  void* stream) {
+  BABE_REQUIRE(X && Xref && coef && (gX || gXref), BABE_EBADARG, "spec_mag_grad: null pointer");
+  BABE_REQUIRE(B >= 1 && F >= 1 && frames >= 1, BABE_EBADARG, "spec_mag_grad: bad shape");
+  const long long n = (long long)B * F * frames;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+  k_spec_mag_grad<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(X), reinterpret_cast<const float2*>(Xref), H, w, coef, F, frames, n,
+      reinterpret_cast<float2*>(gX), reinterpret_cast<float2*>(gXref));
+  return check_launch("k_spec_mag_grad");
 }

@@ -205,6 +205,22 @@ def spec_mag_stats(X, Xref, H=None, w=None):
     return out
 
 
+def spec_mag_grad(X, Xref, H, w, coef, want_X=True, want_Xref=False):
+    """Gradients of || w (H|X| - |Xref|) ||_2 wrt the spectrograms; coef: 1-element CUDA tensor (g / norm)."""
+    X = _cuda_f32(X, "X")
+    Xref = _cuda_f32(Xref, "Xref")
+    B, F, M, _ = X.shape
+    H = None if H is None else _cuda_f32(H, "H")
+    w = None if w is None else _cuda_f32(w, "w")
+    coef = _cuda_f32(coef, "coef").reshape(1)
+    gX = torch.empty_like(X) if want_X else None
+    gR = torch.empty_like(Xref) if want_Xref else None
+    with profiling.op("spec_mag_grad", 1, 4 * X.numel() * (2 + int(want_X) + int(want_Xref))):
+        check(lib().babe_spec_mag_grad(_p(X), _p(Xref), _p(H), _p(w), _p(coef), B, F, M, _p(gX), _p(gR), _stream()),
+              "spec_mag_grad")
+    return gX, gR
+
+
 def fit_params(abc, w, freqs, params, cfg, return_iters=False):
     """Run the device-resident projected gradient descent IN PLACE on
     params[2,K] (float32, CUDA, contiguous)."""

@@ -141,6 +141,11 @@ int babe_stft_stats(const float* x, const float* y, int B, int T, int nfft,
  * a, b, c and s_k = sum_{b,t} (w_k (H_k |X| - |Xref|))^2 (H, w may be NULL = 1). */
 int babe_spec_mag_stats(const float* X, const float* Xref, const float* H, const float* w,
                         int B, int F, int frames, double* out, void* stream);
+/* Gradient of that norm wrt the spectrograms (what autograd gives the reference when X or Xref require grad):
+ * gX = coef w^2 (H|X| - |Xref|) H X/|X|, gXref = -coef w^2 (H|X| - |Xref|) Xref/|Xref|; coef is a 1-element
+ * DEVICE array holding (upstream gradient / norm); either output may be NULL. */
+int babe_spec_mag_grad(const float* X, const float* Xref, const float* H, const float* w, const float* coef,
+                       int B, int F, int frames, float* gX, float* gXref, void* stream);
 
 /* ---- a7: device-resident filter fit ------------------------------------ */
 /* Replaces the Python loop of BlindSampler.fit_params

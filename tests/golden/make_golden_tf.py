@@ -180,9 +180,25 @@ def gen_optional():
     return out
 
 
+def gen_specgrad():
+    """autograd of apply_filter_and_norm_STFTmag_fweighted wrt BOTH spectrograms (utils/blind_bwe_utils.py:250-296)."""
+    g = dict(np.load(os.path.join(HERE, "operator_n1024.npz")))
+    nfft = int(g["nfft"])
+    X = ref_ops.apply_stft(torch.from_numpy(g["x"]), nfft).requires_grad_(True)
+    Y = ref_ops.apply_stft(torch.from_numpy(g["yobs"]), nfft).requires_grad_(True)
+    H = torch.from_numpy(g["H"])
+    out = {}
+    for wk in ("sqrt", "None"):
+        nrm = ref_ops.apply_filter_and_norm_STFTmag_fweighted(X, Y, H, wk)
+        gX, gY = torch.autograd.grad(3.0 * nrm, (X, Y))
+        out[f"specgrad_{wk}_gX"], out[f"specgrad_{wk}_gXref"] = gX, gY
+    return out
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     tf = {}
+    tf.update(gen_specgrad())
     tf.update(gen_fit())
     tf.update(gen_steps())
     np.savez_compressed(os.path.join(HERE, "teacher_forced.npz"), **_np(tf))
