@@ -53,6 +53,8 @@ SIGNATURES = {
     "babe_stft_supported": (c_int, [c_int]),
     "babe_set_fused_variant": (c_int, [c_int]),
     "babe_get_fused_variant": (c_int, []),
+    "babe_set_cqt_variant": (c_int, [c_int]),
+    "babe_get_cqt_variant": (c_int, []),
     "babe_stft_tables_host": (c_int, [c_int, c_void_p, c_void_p]),
     "babe_design_filter": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                    c_void_p, c_void_p, c_void_p]),

@@ -21,6 +21,7 @@
 #include "bandfft.cuh"
 #include "smemfft.cuh"
 #include "rfft_pairs.cuh"
+#include "cqt_fft.cuh"
 
 namespace babe {
 
@@ -204,12 +205,29 @@ __device__ __forceinline__ int find_octave(const BandArgs& a, int item) {
 }
 
 // --- octaves with M = 256 * R3: register FFT (bandfft.cuh), 16 / R3 bands per CTA ----------
+// The 16 input values of a thread for row r+1 (a window slice of the half spectrum, or a coefficient row) are
+// copied global -> shared with 8-byte cp.async while row r is transformed: round 1's version loaded them straight
+// into registers at the top of every row and sat on the scoreboard (long_scoreboard 7.7 of 13 stall cycles per
+// issue, profiles/r01_cqt_B64.md).
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4f(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <int R3, bool SYNTH>
 __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int tile, unsigned char* smem_raw) {
   using C = BandCore<R3>;
   constexpr int NB = BAND_THREADS / C::TPB, M = C::M;
   float2* exs = reinterpret_cast<float2*>(smem_raw);
   float2* tw = exs + NB * C::EX;
+  float2* stage = tw + C::TPB;                         // [16][BAND_THREADS]: slot n1 of thread tid
   const int tid = threadIdx.x, bl = tid / C::TPB, t = tid % C::TPB;
   const float2* roots_m = a.rootsm[o];
   C::load_twiddles(tw, roots_m);
@@ -225,44 +243,77 @@ __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int til
   const int half = lg / 2;
   float2* ex = exs + bl * C::EX;
   const float inv_m = 1.0f / (float)M;
-  __syncthreads();
+  // analysis: window samples (times the optional bin scale) and validity of this thread's 16 slots are
+  // row-independent: kept in shared memory next to the prefetch slots (zero = slot outside the window; those
+  // slots are never copied into, so they are zeroed once)
+  float* wst = reinterpret_cast<float*>(stage + 16 * BAND_THREADS);
+  unsigned valid = 0;
+  if (!SYNTH) {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      int i = C::TPB * n1 + t + half;
+      if (i >= M) i -= M;
+      float w = 0.f;
+      const int k = p - half + i;
+      if (active && i < lg && k >= 0 && k <= a.Nc) {
+        w = a.win[off + i];
+        if (a.scale) w *= a.scale[k];
+        valid |= 1u << n1;
+      }
+      wst[n1 * BAND_THREADS + tid] = w;
+      stage[n1 * BAND_THREADS + tid] = make_float2(0.f, 0.f);
+    }
+  }
+  const int row0 = blockIdx.y * a.rows_per_cta;
   const int row_end = min(a.B, (int)(blockIdx.y + 1) * a.rows_per_cta);
-  for (int row = blockIdx.y * a.rows_per_cta; row < row_end; ++row) {
-    float re[16], im[16];
+  auto prefetch = [&](int row) {
     if (!SYNTH) {
-      // slot m holds window sample i with (i - half) mod M == m, conjugated (inverse FFT via forward)
-      const float2* X = a.X + (size_t)row * (a.Nc + 1);
+      const float2* X = a.X + (size_t)row * (a.Nc + 1) + (p - half);
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         int i = C::TPB * n1 + t + half;
         if (i >= M) i -= M;
-        float2 v = make_float2(0.f, 0.f);
-        if (i < lg) {
-          const int k = p - half + i;
-          if (k >= 0 && k <= a.Nc) {
-            float w = a.win[off + i];
-            if (a.scale) w *= a.scale[k];
-            const float2 xv = X[k];
-            v = make_float2(xv.x * w, -xv.y * w);
-          }
-        }
-        re[n1] = v.x; im[n1] = v.y;
+        if (valid & (1u << n1)) cp_async8(stage + n1 * BAND_THREADS + tid, X + i);
       }
     } else if (active) {
       if (!a.planar) {
         const float2* in = a.coef[o] + ((size_t)row * a.binsoct + band) * M;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) { const float2 v = in[C::TPB * n1 + t]; re[n1] = v.x; im[n1] = v.y; }
+        for (int n1 = 0; n1 < 16; ++n1) cp_async8(stage + n1 * BAND_THREADS + tid, in + C::TPB * n1 + t);
       } else {
         const float* ire = reinterpret_cast<const float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + band) * M;
         const float* iim = ire + (size_t)a.binsoct * M;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) { re[n1] = ire[C::TPB * n1 + t]; im[n1] = iim[C::TPB * n1 + t]; }
+        for (int n1 = 0; n1 < 16; ++n1) {
+          float* d = reinterpret_cast<float*>(stage + n1 * BAND_THREADS + tid);
+          cp_async4f(d, ire + C::TPB * n1 + t);
+          cp_async4f(d + 1, iim + C::TPB * n1 + t);
+        }
       }
+    }
+  };
+  if (row0 < row_end) prefetch(row0);
+  __syncthreads();
+  for (int row = row0; row < row_end; ++row) {
+    float re[16], im[16];
+    cp_async_commit_wait();                       // this thread's own copies: no barrier needed to read them
+    if (!SYNTH) {
+      // slot m holds window sample i with (i - half) mod M == m, conjugated (inverse FFT via forward)
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const float2 xv = stage[n1 * BAND_THREADS + tid];
+        const float w = wst[n1 * BAND_THREADS + tid];
+        re[n1] = xv.x * w;
+        im[n1] = -xv.y * w;
+      }
+    } else if (active) {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) { const float2 v = stage[n1 * BAND_THREADS + tid]; re[n1] = v.x; im[n1] = v.y; }
     } else {
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) { re[n1] = 0.f; im[n1] = 0.f; }
     }
+    if (row + 1 < row_end) prefetch(row + 1);     // the staged values are in registers: the slots are free
     C::fwd(re, im, ex, tw, rg, t);
     if (active) {
       if (!SYNTH) {
@@ -491,8 +542,9 @@ static int validate_plan(const babe_cqt_plan* p, bool bands) {
   BABE_REQUIRE(p->roots1 && p->roots2 && p->tw_nc && p->tw_ls, BABE_EBADARG, "plan tables missing");
   const size_t smem1 = sizeof(float2) * ((size_t)2 * TILE_SEQ * odd_stride(p->f1.n) + p->f1.n + TW_LO + (p->Nc >> 10) + 1);
   const size_t smem2 = sizeof(float2) * ((size_t)2 * TILE_SEQ * odd_stride(p->f2.n) + p->f2.n);
-  BABE_REQUIRE(smem1 <= 220 * 1024 && smem2 <= 220 * 1024, BABE_EUNSUPPORTED,
-               "pass lengths %d x %d do not fit shared memory", p->f1.n, p->f2.n);
+  BABE_REQUIRE((smem1 <= 220 * 1024 && smem2 <= 220 * 1024) ||
+                   (tile_fft_smem(p->f1.n) <= 220 * 1024 && tile_fft_smem(p->f2.n) <= 220 * 1024),
+               BABE_EUNSUPPORTED, "pass lengths %d x %d do not fit shared memory", p->f1.n, p->f2.n);
   if (bands) {
     BABE_REQUIRE(p->numocts >= 1 && p->numocts <= BABE_MAX_OCTAVES && p->binsoct >= 1, BABE_EBADARG,
                  "bad octave layout");
@@ -549,6 +601,85 @@ static int big_fft(const babe_cqt_plan* p, const float2* in, float2* tmp, float2
   return check_launch("k_fft_rows");
 }
 
+
+// ---- second-generation length-Ls transform (cqt_fft.cuh) ---------------------------------------------------
+// 0: tiled passes with fused r2c / c2r / gather (cqt_fft.cuh); -1: round-1 passes.  Measured on B200 (profiles/
+// r02_cqt.md): the tiled passes need 128 registers for the radix-13 / 23 butterflies (2 CTAs per SM) and come out
+// 7-40 % SLOWER than the round-1 passes (80 registers, 3 CTAs per SM) despite two launches fewer, so round 1's are
+// the default.
+static int g_cqt_variant = -1;
+static bool tiled_ok(const babe_cqt_plan* p) {
+  return g_cqt_variant >= 0 && tile_fft_smem(p->f1.n) <= 220 * 1024 && tile_fft_smem(p->f2.n) <= 220 * 1024;
+}
+
+static int launch_f1(const babe_cqt_plan* p, const float2* in, float2* out, int B, int twiddle, int conj_out,
+                     cudaStream_t st) {
+  F1Args a{};
+  a.in = in; a.out = out; a.Nc = p->Nc; a.N1 = p->f1.n; a.N2 = p->f2.n;
+  a.f = to_dev(p->f1); a.roots = reinterpret_cast<const float2*>(p->roots1);
+  a.tw_nc = reinterpret_cast<const float2*>(p->tw_nc);
+  a.twiddle = twiddle; a.conj_out = conj_out;
+  const size_t smem = tile_fft_smem(a.N1);
+  cudaFuncSetAttribute(k_fft_n1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fft_n1<<<dim3((a.N2 + TF_SEQ - 1) / TF_SEQ, B), TF_THREADS, smem, st>>>(a);
+  return check_launch("k_fft_n1");
+}
+
+static F2Args f2_args(const babe_cqt_plan* p, const float* scale) {
+  F2Args a{};
+  a.Nc = p->Nc; a.N1 = p->f1.n; a.N2 = p->f2.n;
+  a.f = to_dev(p->f2); a.roots = reinterpret_cast<const float2*>(p->roots2);
+  a.tw_nc = reinterpret_cast<const float2*>(p->tw_nc);
+  a.tw_ls = reinterpret_cast<const float2*>(p->tw_ls);
+  a.scale = scale;
+  return a;
+}
+static int f2_grid(int N1) { return ((N1 - 1) / 2 + 7) / 8 + 1; }
+
+// Y[N1][N2] -> half spectrum X[Nc+1] (times scale)
+static int launch_f2_fwd(const babe_cqt_plan* p, const float2* Y, float2* X, const float* scale, int B,
+                         cudaStream_t st) {
+  F2Args a = f2_args(p, scale);
+  a.Y = Y; a.Xout = X;
+  const size_t smem = tile_fft_smem(a.N2);
+  cudaFuncSetAttribute(k_fft_n2_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fft_n2_fwd<<<dim3(f2_grid(a.N1), B), TF_THREADS, smem, st>>>(a);
+  return check_launch("k_fft_n2_fwd");
+}
+
+// half spectrum X[Nc+1] (times scale), or the synthesis band spectra BS (gather), -> Y[N1][N2]
+static int launch_f2_inv(const babe_cqt_plan* p, const float2* X, const float2* BS, float2* Y, const float* scale,
+                         int B, cudaStream_t st) {
+  F2Args a = f2_args(p, scale);
+  a.X = X; a.Yout = Y;
+  const size_t smem = tile_fft_smem(a.N2);
+  if (BS != nullptr) {
+    a.BS = BS; a.sum_lg = p->sum_lg;
+    a.band_p = p->band_p; a.band_lg = p->band_lg; a.band_off = p->band_off; a.jlo = p->bin_jlo; a.jhi = p->bin_jhi;
+    cudaFuncSetAttribute(k_fft_n2_inv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fft_n2_inv<true><<<dim3(f2_grid(a.N1), B), TF_THREADS, smem, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(k_fft_n2_inv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fft_n2_inv<false><<<dim3(f2_grid(a.N1), B), TF_THREADS, smem, st>>>(a);
+  }
+  return check_launch("k_fft_n2_inv");
+}
+
+// x[B, Ls] real -> X[B, Nc+1]  (two launches)
+static int tiled_rfft(const babe_cqt_plan* p, const float2* x, float2* tmp, float2* X, const float* scale, int B,
+                      cudaStream_t st) {
+  int rc = launch_f1(p, x, tmp, B, 1, 0, st);
+  if (rc) return rc;
+  return launch_f2_fwd(p, tmp, X, scale, B, st);
+}
+// X[B, Nc+1] (or band spectra) -> x[B, Ls] real  (two launches)
+static int tiled_irfft(const babe_cqt_plan* p, const float2* X, const float2* BS, float2* tmp, float2* x,
+                       const float* scale, int B, cudaStream_t st) {
+  int rc = launch_f2_inv(p, X, BS, tmp, scale, B, st);
+  if (rc) return rc;
+  return launch_f1(p, tmp, x, B, 0, 1, st);
+}
+
 static inline int band_r3(int M) {     // M = 256 * R3 handled by BandCore<R3>, else 0
   switch (M) { case 256: return 1; case 512: return 2; case 1024: return 4; case 2048: return 8;
                case 4096: return 16; default: return 0; }
@@ -566,7 +697,8 @@ static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int
     size_t need;
     if (r3) {                                  // register FFT: 4096 points per CTA
       tb = 16 / r3;
-      need = sizeof(float2) * ((size_t)tb * 16 * (16 * r3 + 1) + 16 * r3);
+      need = sizeof(float2) * ((size_t)tb * 16 * (16 * r3 + 1) + 16 * r3 + 16 * BAND_THREADS) +
+             sizeof(float) * 16 * BAND_THREADS;   // ex + twiddles + prefetch stage + window samples
     } else {                                   // shared-memory Stockham: <= 2048 points per CTA
       tb = std::max(1, std::min(std::min(p->binsoct, MAX_TB), 2048 / M));
       need = sizeof(float2) * ((size_t)2 * tb * odd_stride(M) + M);
@@ -604,6 +736,8 @@ extern "C" int babe_rfft(const babe_cqt_plan* plan, const float* x, float* X, in
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tiled_ok(plan))
+    return tiled_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, reinterpret_cast<float2*>(X), bin_scale, B, st);
   rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
   if (rc) return rc;
   const int n = plan->Nc / 2 + 1;
@@ -623,6 +757,9 @@ extern "C" int babe_irfft(const babe_cqt_plan* plan, const float* X, float* x, i
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tiled_ok(plan))
+    return tiled_irfft(plan, reinterpret_cast<const float2*>(X), nullptr, w.bufA, reinterpret_cast<float2*>(x),
+                       bin_scale, B, st);
   const int n = plan->Nc / 2 + 1;
   k_irfft_pre<<<dim3((n + 255) / 256, B), 256, 0, st>>>(reinterpret_cast<const float2*>(X), w.bufA,
                                                         plan->Nc,
@@ -643,6 +780,11 @@ extern "C" int babe_spectral_filter(const babe_cqt_plan* plan, const float* x, f
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tiled_ok(plan)) {
+    rc = tiled_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufX, H, B, st);
+    if (rc) return rc;
+    return tiled_irfft(plan, w.bufX, nullptr, w.bufA, reinterpret_cast<float2*>(y), nullptr, B, st);
+  }
   rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
   if (rc) return rc;
   const int n = plan->Nc / 2 + 1;
@@ -664,14 +806,19 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
-  if (rc) return rc;
-  const int n = plan->Nc / 2 + 1;
-  k_rfft_post<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bufB, w.bufX, plan->Nc,
-                                                        reinterpret_cast<const float2*>(plan->tw_ls),
-                                                        nullptr);
-  rc = check_launch("k_rfft_post");
-  if (rc) return rc;
+  if (tiled_ok(plan)) {
+    rc = tiled_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufX, nullptr, B, st);
+    if (rc) return rc;
+  } else {
+    rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
+    if (rc) return rc;
+    const int n = plan->Nc / 2 + 1;
+    k_rfft_post<<<dim3((n + 255) / 256, B), 256, 0, st>>>(w.bufB, w.bufX, plan->Nc,
+                                                          reinterpret_cast<const float2*>(plan->tw_ls),
+                                                          nullptr);
+    rc = check_launch("k_rfft_post");
+    if (rc) return rc;
+  }
   BandArgs a{};
   size_t smem;
   int items;
@@ -710,6 +857,8 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
   k_cqt_synth_bands<<<dim3(items, (B + a.rows_per_cta - 1) / a.rows_per_cta), BAND_THREADS, smem, st>>>(a);
   rc = check_launch("k_cqt_synth_bands");
   if (rc) return rc;
+  if (tiled_ok(plan))       // overlap-add gather + c2r pre-processing in the prologue of the inverse's first pass
+    return tiled_irfft(plan, nullptr, w.bufS, w.bufA, reinterpret_cast<float2*>(x), bin_scale, B, st);
   GatherArgs g{};
   g.BS = w.bufS; g.Zc = w.bufA; g.Nc = plan->Nc; g.sum_lg = plan->sum_lg;
   g.band_p = plan->band_p; g.band_lg = plan->band_lg; g.band_off = plan->band_off;
@@ -721,3 +870,11 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
   if (rc) return rc;
   return big_fft(plan, w.bufA, w.bufB, reinterpret_cast<float2*>(x), B, 1, st);
 }
+
+// profiling / A-B knob (profiles/probe_r02.py): which implementation computes the length-Ls transform
+extern "C" int babe_set_cqt_variant(int v) {
+  if (v < -1 || v > 0) return BABE_EBADARG;
+  babe::g_cqt_variant = v;
+  return BABE_OK;
+}
+extern "C" int babe_get_cqt_variant(void) { return babe::g_cqt_variant; }

@@ -73,6 +73,14 @@ int babe_design_filter_vjp(const float* fc, const float* A, int K, const float* 
  * Process-wide, not thread-safe against concurrent launches. */
 int babe_set_fused_variant(int variant);
 int babe_get_fused_variant(void);
+/* Which implementation computes the length-Ls real FFT / inverse of the CQT calls (babe_rfft, babe_irfft,
+ * babe_spectral_filter, babe_cqt_analysis, babe_cqt_synthesis):
+ *    0            tiled passes (csrc/cqt_fft.cuh): 16 sequences per CTA held [element][sequence], the r2c post-,
+ *                 c2r pre-processing and the synthesis overlap-add gather fused into the passes (2 launches per
+ *                 transform); measured 7-40 % slower on B200 (profiles/r02_cqt.md), kept for A/B;
+ *   -1 (default)  the round-1 passes with separate post / pre / gather kernels. */
+int babe_set_cqt_variant(int variant);
+int babe_get_cqt_variant(void);
 
 /* ---- a3/a12: fused STFT -> H -> iSTFT ---------------------------------- */
 /* Replaces apply_filter (utils/blind_bwe_utils.py:6-13) and
