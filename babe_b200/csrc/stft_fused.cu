@@ -512,9 +512,11 @@ int launch_stats_fused(FusedStatsArgs a, int* n_partials, cudaStream_t st) {
 }  // namespace babe
 
 // profiling / A-B knob (profiles/probe_r02.py): which implementation serves NFFT = 4096
+namespace babe { void set_fit_variant(int v); }
 extern "C" int babe_set_fused_variant(int v) {
   if (v < -1 || v > 0) return BABE_EBADARG;
   babe::g_fused_variant = v;
+  babe::set_fit_variant(v);
   return BABE_OK;
 }
 extern "C" int babe_get_fused_variant(void) { return babe::g_fused_variant; }

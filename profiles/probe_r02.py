@@ -143,3 +143,28 @@ def time_cqt():
 
 if __name__ == "__main__" and "cqt" in sys.argv[1:]:
     time_cqt()
+
+
+def time_fit():
+    from babe_b200 import sampler
+    x8 = torch.randn(8, 184184, device=dev) * 0.063
+    y8 = ops.apply_filter(x8, NFFT, freqs=f, fc=torch.tensor([1000.0], device=dev), A=torch.tensor([-20.0], device=dev))
+    fit = sampler.FilterFit(nfft=NFFT, sample_rate=SR, device=dev)
+    abc = fit.stats(x8, y8)
+    for K, p0 in ((5, [[280.0, 285, 290, 295, 300], [-15.0, -17, -20, -25, -30]]),
+                  (7, [[200.0, 225, 250, 275, 300, 325, 350], [-15.0, -20, -25, -30, -40, -50, -55]])):
+        p0 = torch.tensor(p0, device=dev)
+        res = {}
+        for v in (-1, 0):
+            lib().babe_set_fused_variant(v)
+            med, best = timeit(lambda: fit(x8, y8, p0.clone(), abc=abc), iters=20)
+            p, its = fit(x8, y8, p0.clone(), abc=abc, return_iters=True)
+            res[v] = p.clone()
+            print(json.dumps({"op": "fit_params", "K": K, "variant": v, "ms": round(med, 4), "best_ms": round(best, 4),
+                              "iters": int(its)}))
+        print("  max rel diff new vs round-1:", rel(res[0], res[-1]))
+    lib().babe_set_fused_variant(0)
+
+
+if __name__ == "__main__" and "fit" in sys.argv[1:]:
+    time_fit()
