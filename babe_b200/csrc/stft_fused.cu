@@ -431,6 +431,129 @@ __global__ void __launch_bounds__(256, 2) k_stats_fused(const FusedStatsArgs a) 
 }
 
 // ---------------------------------------------------------------------------
+// FIR "same" convolution by overlap-save on Core4k (predict_bwe("firwin"),
+// testing/blind_bwe_sampler.py:211-218, utils/bandwidth_extension.py:76-95).  torch conv1d is a correlation:
+//   y[n] = sum_k b[k] x[n + k - pl],  pl = (L-1)/2.  A block of V = N - L + 1 outputs needs N inputs; two consecutive
+// blocks ride one complex transform and the packed spectrum is multiplied by G = conj(FFT(taps)) / N (host-prepared,
+// permuted into the [k3][thread] order of Core4k once per CTA).  Both input windows are staged by bulk TMA copies:
+// their starts are arbitrary sample positions, so each copy begins at the 16-byte boundary below the window and
+// the readers add the remainder.
+// ---------------------------------------------------------------------------
+constexpr int FIR_STAGE = Core4k::N + 8;        // floats per staged window (4096 + alignment slack, 16-byte multiple)
+
+constexpr size_t fir_smem_bytes() {
+  return sizeof(float2) * (256 + Core4k::N + Core4k::EX) + sizeof(float) * 2 * FIR_STAGE + 32;
+}
+
+// window [a0, a0 + N) of a row of length T into `dst` such that sample a0 + n sits at dst[off + n];
+// returns off (0..3); positions outside [0, T) are left untouched (the readers mask them)
+__device__ __forceinline__ int fir_issue(float* dst, uint64_t* bar, const float* xr, int T, long long a0,
+                                         uint32_t* bytes_out) {
+  long long lo = a0 >= 0 ? (a0 & ~3LL) : -(((-a0) + 3) & ~3LL);      // 16-byte boundary at or below a0
+  const int off = (int)(a0 - lo);
+  long long hi = a0 + Core4k::N;                                   // one past the last sample needed
+  hi = (hi + 3) & ~3LL;
+  long long c0 = lo < 0 ? 0 : lo, c1 = hi > T ? T : hi;              // clipped to the row (T % 4 == 0)
+  uint32_t bytes = c1 > c0 ? (uint32_t)(c1 - c0) * 4u : 0u;
+  if (bytes) bulk_g2s(dst + (c0 - lo), xr + c0, bytes, bar);
+  *bytes_out = bytes;
+  return off;
+}
+
+__global__ void __launch_bounds__(256, 2) k_fir_fused(const FusedFirArgs a) {
+  using C = Core4k;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* tw3 = reinterpret_cast<float2*>(smem_raw);
+  float2* gp = tw3 + 256;                          // G permuted: entry 256 k3 + t = G[bin_of(t, k3)]
+  float2* ex = gp + C::N;
+  float* stage = reinterpret_cast<float*>(ex + C::EX);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(stage + 2 * FIR_STAGE);
+  const int t = threadIdx.x;
+  tw3[t] = a.roots[(16 * (t >> 4) * (t & 15)) & (C::N - 1)];
+#pragma unroll
+  for (int k3 = 0; k3 < 16; ++k3) gp[256 * k3 + t] = a.G[C::bin_of(t, k3)];
+  if (t == 0) {
+    mbar_init(mbar, 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  C::TwRegs tw;
+  tw.init(a.roots, t);
+  uint32_t phase = 0;
+  const long long total = (long long)a.B * a.pairs_per_row;
+  const long long i0 = (long long)blockIdx.x * a.q;
+  const long long i1 = i0 + a.q < total ? i0 + a.q : total;
+  auto issue = [&](long long item) {
+    const int row = (int)(item / a.pairs_per_row);
+    const long long s0 = (item - (long long)row * a.pairs_per_row) * 2 * a.V;
+    const float* xr = a.x + (size_t)row * a.T;
+    uint32_t b0, b1;
+    // expect the total first: the byte counts are known before either copy is issued
+    {
+      long long aA = s0 - a.pl, aB = aA + a.V;
+      auto nbytes = [&](long long a0) {
+        long long lo = a0 >= 0 ? (a0 & ~3LL) : -(((-a0) + 3) & ~3LL);
+        long long hi = (a0 + C::N + 3) & ~3LL;
+        long long c0 = lo < 0 ? 0 : lo, c1 = hi > a.T ? a.T : hi;
+        return c1 > c0 ? (uint32_t)(c1 - c0) * 4u : 0u;
+      };
+      const uint32_t tot = nbytes(aA) + nbytes(aB);
+      if (tot) mbar_arrive_tx(mbar, tot); else mbar_arrive(mbar);
+      fir_issue(stage, mbar, xr, a.T, aA, &b0);
+      fir_issue(stage + FIR_STAGE, mbar, xr, a.T, aB, &b1);
+    }
+  };
+  if (t == 0 && i0 < i1) issue(i0);
+  for (long long item = i0; item < i1; ++item) {
+    const int row = (int)(item / a.pairs_per_row);
+    const long long s0 = (item - (long long)row * a.pairs_per_row) * 2 * a.V;
+    float* yr = a.y + (size_t)row * a.T;
+    float2 z[16];
+    {
+      const long long aA = s0 - a.pl, aB = aA + a.V;
+      const long long loA = aA >= 0 ? (aA & ~3LL) : -(((-aA) + 3) & ~3LL);
+      const long long loB = aB >= 0 ? (aB & ~3LL) : -(((-aB) + 3) & ~3LL);
+      const int offA = (int)(aA - loA), offB = (int)(aB - loB);
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const long long pa = aA + 256 * j + t, pb = aB + 256 * j + t;
+        const float va = stage[offA + 256 * j + t], vb = stage[FIR_STAGE + offB + 256 * j + t];
+        z[j] = make_float2((pa >= 0 && pa < a.T) ? va : 0.f, (pb >= 0 && pb < a.T) ? vb : 0.f);
+      }
+    }
+    C::fwd_p1(z, ex, tw, t);
+    group_sync<256>(1);
+    if (t == 0 && item + 1 < i1) issue(item + 1);        // every thread has read the stage
+    C::fwd_p2_load(z, ex, t);
+    __syncwarp();
+    C::fwd_p2_store(z, ex, t);
+    __syncwarp();
+    C::fwd_p3(z, ex, tw3, t);
+#pragma unroll
+    for (int k3 = 0; k3 < 16; ++k3) z[k3] = c_mul(z[k3], gp[256 * k3 + t]);
+    C::inv_q1(z, ex, tw3, t);
+    __syncwarp();
+    C::inv_q2_load(z, ex, t);
+    __syncwarp();
+    C::inv_q2_store(z, ex, t);
+    group_sync<256>(1);
+    C::inv_q3(z, ex, tw, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = 256 * j + t;
+      if (n < a.V) {
+        const long long pa = s0 + n, pb = pa + a.V;
+        if (pa < a.T) yr[pa] = z[j].x;
+        if (pb < a.T) yr[pb] = z[j].y;
+      }
+    }
+    group_sync<256>(1);                                  // ex may be overwritten
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 static int g_fused_variant = 0;     // 0: fused kernels (this file); -1: round-1 kernels (stft_ops.cu)
@@ -507,6 +630,23 @@ int launch_stats_fused(FusedStatsArgs a, int* n_partials, cudaStream_t st) {
   cudaFuncSetAttribute(k_stats_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_stats_fused<<<grid, 256, smem, st>>>(a);
   return check_launch("k_stats_fused");
+}
+
+bool fused_fir_eligible(const float* x, int T) {
+  return g_fused_variant >= 0 && (T % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+int launch_fir_fused(FusedFirArgs a, cudaStream_t st) {
+  const long long total = (long long)a.B * a.pairs_per_row;
+  const long long ctas = 2LL * sm_count();
+  long long q = (total + ctas - 1) / ctas;
+  if (q < 1) q = 1;
+  a.q = (int)q;
+  const int grid = (int)((total + q - 1) / q);
+  constexpr size_t smem = fir_smem_bytes();
+  cudaFuncSetAttribute(k_fir_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_fir_fused<<<grid, 256, smem, st>>>(a);
+  return check_launch("k_fir_fused");
 }
 
 }  // namespace babe

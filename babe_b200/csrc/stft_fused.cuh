@@ -31,4 +31,13 @@ bool fused_stats_eligible(const float* x, const float* y, int T, int mode);
 // launches k_stats_fused; *n_partials = rows of `partial` written (<= 2 * SM count)
 int launch_stats_fused(FusedStatsArgs a, int* n_partials, cudaStream_t st);
 
+struct FusedFirArgs {
+  const float* x; float* y; int B, T;
+  const float2* roots; const float2* G;                 // G[N] = conj(FFT(taps zero padded)) / N, natural bin order
+  int L, pl, V, pairs_per_row;
+  int q;                                                // filled by the launcher (block pairs per CTA)
+};
+bool fused_fir_eligible(const float* x, int T);
+int launch_fir_fused(FusedFirArgs a, cudaStream_t st);
+
 }  // namespace babe

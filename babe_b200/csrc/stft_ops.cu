@@ -944,6 +944,12 @@ extern "C" int babe_fir_filter(const float* x, float* y, int B, int T, const flo
   a.L = L; a.pl = pad_left; a.V = Core3::N - L + 1;
   const int blocks = (T + a.V - 1) / a.V;
   a.pairs_per_row = (blocks + 1) / 2;
+  if (fused_fir_eligible(x, T)) {       // second-generation kernel: TMA-staged windows, Core4k (stft_fused.cu)
+    FusedFirArgs f{};
+    f.x = x; f.y = y; f.B = B; f.T = T; f.roots = a.twiddle; f.G = a.G;
+    f.L = L; f.pl = pad_left; f.V = a.V; f.pairs_per_row = a.pairs_per_row;
+    return launch_fir_fused(f, static_cast<cudaStream_t>(stream));
+  }
   const long long items = (long long)B * a.pairs_per_row;
   const int grid = (int)std::min<long long>(items, (long long)sm_count() * Core3::MIN_CTAS);
   const size_t smem = sizeof(float2) * (Core3::TW_SMEM + Core3::EX_ELEMS);

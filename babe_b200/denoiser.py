@@ -5,9 +5,12 @@ denoiser's convolutions stay in PyTorch", BASELINE.json); it is restated here
 only because the sampler benchmark needs the named model on machines where the
 reference tree does not exist.  Architecture, constructor order (hence the
 random initialisation under a fixed seed) and state-dict keys follow
-``networks/cqtdiff+.py`` (Unet_CQT_oct_with_attention, :583-845) so reference
-checkpoints load unchanged; attention layers (all disabled in
-conf/network/cqtdiff+.yaml:27) are not implemented.
+``networks/cqtdiff+.py`` (Unet_CQT_oct_with_attention, :583-845), so a reference
+state dict LOADS key for key (tests/test_denoiser_cpu.py, tests/test_integration_*.py).  Whether pretrained
+weights then BEHAVE as trained depends on the constant-Q transform around the body: upstream's
+``cqt_nsgt_pytorch`` is not available offline and the in-repo transform follows its own specification
+(oracle/nsgt.py, parity unpinned) -- validate a checkpoint before relying on it.  Attention layers (all
+disabled in conf/network/cqtdiff+.yaml:27) are not implemented.
 
 Execution differences that do not change the mathematics: the x2 time
 resamplers run as single-channel FIR convolutions instead of rebuilding a dense

@@ -91,6 +91,7 @@ class FilterFit:
                  max_iter=100, tol=(5e-3, 5e-3), mu=(1000, 10), clamp_fc=True, clamp_A=True,
                  only_negative_A=True, freq_weighting="sqrt", device="cuda"):
         self.nfft = int(nfft)
+        self.sample_rate, self.freq_weighting = sample_rate, str(freq_weighting)
         fcmax_v = sample_rate // 2 if fcmax == "nyquist" else fcmax   # :35-38 (integer division)
         self.cfg = FitConfig(mu_fc=mu[0], mu_A=mu[1], fcmin=fcmin, fcmax=fcmax_v, Amin=Amin, Amax=Amax,
                              tol_fc=tol[0], tol_A=tol[1], max_iter=int(max_iter),
@@ -108,6 +109,11 @@ class FilterFit:
                    Amin=b.Amin, Amax=b.Amax, max_iter=o.max_iter, tol=o.tol, mu=o.mu,
                    clamp_fc=o.clamp_fc, clamp_A=o.clamp_A, only_negative_A=o.only_negative_A,
                    freq_weighting=args.tester.posterior_sampling.freq_weighting_filter, device=device)
+
+    def cfg_key(self):
+        c = self.cfg
+        return (self.nfft, self.sample_rate, self.freq_weighting, c.mu_fc, c.mu_A, c.fcmin, c.fcmax, c.Amin, c.Amax, c.tol_fc, c.tol_A, c.max_iter,
+                c.clamp_fc, c.clamp_A, c.only_negative_A)
 
     def stats(self, x_den, y):
         return ops.stft_stats(x_den, y, self.nfft, mode=0)
@@ -154,6 +160,9 @@ def rec_guidance_norms(x, y, freqs, filter_params, nfft):
                                   filter_params[1].contiguous(), int(nfft))
 
 
+_PINNED_NOISE = {}
+
+
 # ---------------------------------------------------------------------------
 class BlindSamplerFused:
     def __init__(self, model, diff_params, args, rid=False, device_noise=False, freeze_model=True,
@@ -168,6 +177,11 @@ class BlindSamplerFused:
         # shapes, frozen parameters, no host synchronisation inside the network)
         self.cuda_graph = cuda_graph
         self._graphed, self._graph_key, self._graph_launches = None, None, (0, 0)
+        # SURVEY 8f-1, whole step: ONE captured CUDA graph per sampler step (stochastic move, denoiser forward and
+        # backward, fit statistics + fit loop, fused guidance, Heun correction with its second evaluation, state
+        # update); the schedule scalars are device tensors, nothing is launched eagerly between two replays
+        self.step_graph = False
+        self._step_graphs, self._step_key = {}, None
         self.diff_params = diff_params
         self.args = args
         if not args.tester.diff_params.same_as_training:
@@ -205,8 +219,8 @@ class BlindSamplerFused:
         """The reference's ``torch.randn(shape).to(device)`` -- same host generator stream, same values --
         drawn into one of two page-locked staging buffers and copied asynchronously (a pageable source makes
         the copy synchronous and ~2x slower)."""
-        ring = self.__dict__.setdefault("_noise_ring", {})
-        slot = ring.get(shape)
+        ring = _PINNED_NOISE                       # process-wide: pinning is expensive, and freeing pinned memory
+        slot = ring.get(shape)                     # while a CUDA graph is being captured invalidates the capture
         if slot is None:
             slot = ring[shape] = {"bufs": [torch.empty(shape, pin_memory=True) for _ in range(2)],
                                   "events": [None, None], "i": 0}
@@ -367,6 +381,73 @@ class BlindSamplerFused:
                 grads[i, j, 0], grads[i, j, 1], norms[i, j] = gfc[0], gA[0], nrm
         return norms, grads
 
+    # -- one sampler step as a pure function of device tensors ----------------------------------------
+    def _step_math(self, x, filter_params, eps, t_i, gamma_i, t_next, y, heun):
+        """Lines :686-:761 of the reference loop; all scalars are 0-d device tensors."""
+        t_hat = t_i + gamma_i * t_i
+        x_hat = x + ((t_hat ** 2 - t_i ** 2) ** (1 / 2)) * eps
+        score, filter_params, x_den_2 = self._evaluate(x_hat, t_hat, y, filter_params)
+        fp_mid = filter_params.clone()           # what rid logs (:724): the filter after the FIRST evaluation
+        d = -t_hat * score
+        h = t_next - t_hat
+        if heun:
+            x_prime = x_hat + h * d
+            score, filter_params, _ = self._evaluate(x_prime, t_next, y, filter_params)
+            x_new = x_hat + h * ((1 / 2) * d + (1 / 2) * (-t_next * score))
+        else:
+            x_new = x_hat + h * d
+        return x_new, filter_params, x_den_2, fp_mid
+
+    def _step_graph_for(self, y, filter_params, heun):
+        """Capture (once per shape / variant) and return the replayable step."""
+        key = (tuple(y.shape), y.device, tuple(filter_params.shape), self._fit.cfg_key())
+        if self._step_key != key:
+            self._step_key, self._step_graphs = key, {}
+        if heun in self._step_graphs:
+            st = self._step_graphs[heun]
+            st.y.copy_(y)
+            return st
+        dev = y.device
+        # everything the captured kernels read by address is owned by the graph state: the observations are copied
+        # into a static buffer, and the fit object (frequency / weight tables) of the capturing call is kept alive
+        # and re-installed on replaying calls
+        st = types.SimpleNamespace(
+            y=y.clone(), fit=self._fit, freqs=self.freqs,
+            x=torch.zeros_like(y), fp=filter_params.clone(), eps=torch.zeros_like(y),
+            t_i=torch.ones((), device=dev), gamma=torch.zeros((), device=dev), t_next=torch.ones((), device=dev) * 0.5,
+            graph=None, x_out=None, fp_out=None, den=None, launches=0)
+        was_prof = profiling._enabled
+        profiling.enable(False)                      # no event records inside a capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                       # warm-up: cuDNN autotuning, lazy tables, allocator pools
+                fp = st.fp.clone()
+                l0 = profiling.launches()
+                self._step_math(st.x, fp, st.eps, st.t_i, st.gamma, st.t_next, st.y, heun)
+                st.launches = profiling.launches() - l0
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        import gc
+        gc.collect()                                 # nothing may be freed behind the capture's back (a pinned
+        gc_was = gc.isenabled()                      # buffer released by the collector queries CUDA events)
+        gc.disable()
+        try:
+            with torch.cuda.graph(g, capture_error_mode="relaxed"):
+                x_new, fp_new, den, fp_mid = self._step_math(st.x, st.fp, st.eps, st.t_i, st.gamma, st.t_next, st.y, heun)
+                st.x.copy_(x_new)                    # the state lives in the static buffers across replays
+                if fp_new.data_ptr() != st.fp.data_ptr():
+                    st.fp.copy_(fp_new)
+                st.den, st.fp_mid = den, fp_mid
+        finally:
+            if gc_was:
+                gc.enable()
+        st.graph = g
+        profiling.enable(was_prof)
+        self._step_graphs[heun] = st
+        return st
+
     # -- the sampling loop ---------------------------------------------------
     def predict_blind_bwe(self, y, rid=False, compute_sweep=False, max_steps=None, step_hook=None,
                           start_step=0, init_x=None, init_params=None):
@@ -405,6 +486,43 @@ class BlindSamplerFused:
         gamma = self.diff_params.get_gamma(t).to(device)
         t_host = t.cpu()
         n_steps = self.nb_steps if max_steps is None else min(start_step + max_steps, self.nb_steps)
+
+        use_step_graph = (self.step_graph and y.is_cuda and not compute_sweep and not self.joint
+                          and not self.cuda_graph
+                          and args.tester.posterior_sampling.SNR_observations == "None"
+                          and not args.tester.blind_bwe.sigma_den_estimate)
+        if use_step_graph:
+            try:
+                self._step_graph_for(y, filter_params, True)
+                self._step_graph_for(y, filter_params, False)
+            except Exception as exc:                       # noqa: BLE001 - any capture problem: stay eager
+                warnings.warn(f"CUDA-graph capture of the sampler step failed ({exc!r}); running it eagerly")
+                use_step_graph = False
+                self._step_graphs = {}
+        if use_step_graph:
+            Snoise = 1
+            for i in range(start_step, n_steps):
+                heun = float(t_host[i + 1]) != 0 and self.order == 2
+                st = self._step_graphs[heun]
+                if i == start_step:
+                    for sg in self._step_graphs.values():
+                        sg.fp.copy_(filter_params)
+                st.x.copy_(x)
+                st.eps.copy_(self._randn(shape, device) * Snoise, non_blocking=True)
+                st.t_i.copy_(t[i]); st.gamma.copy_(gamma[i]); st.t_next.copy_(t[i + 1])
+                st.graph.replay()
+                profiling.add_launches(st.launches)
+                x, filter_params = st.x, st.fp
+                other = self._step_graphs[not heun]
+                if other is not st:
+                    other.fp.copy_(st.fp)
+                if rid:
+                    data_denoised[i] = st.den
+                    data_filters[i] = st.fp_mid
+                if step_hook is not None:
+                    step_hook(i, x, filter_params)
+            x, filter_params = x.clone(), filter_params.clone()
+            n_steps = start_step                           # the eager loop below has nothing left to do
 
         for i in range(start_step, n_steps):
             x_hat, t_hat = self.move_timestep(x, t[i], gamma[i])
@@ -503,17 +621,21 @@ class BlindSamplerFused:
                 new[i:i + size] = left
         return new.unsqueeze(0).expand(B, -1)
 
-    def _generic_rec_grads(self, x_den, y, x_in, t_in, degradation):
-        """get_rec_grads (:75-135) for an arbitrary differentiable degradation (2-norm branch)."""
+    def _generic_rec_grads(self, x_den, y, x_in, t_in, degradation, fused_params=None):
+        """get_rec_grads (:75-135) for an arbitrary differentiable degradation (2-norm branch); a parametric
+        fc_A filter (``fused_params``) takes the fused design + filter + residual-norm kernels."""
         ps = self.args.tester.posterior_sampling
         if ps.SNR_observations != "None" or ps.stft_distance.use or ps.norm not in (1, 2, "fro"):
             raise NotImplementedError("generic degradations support the plain 1-/2-norm guidance")
-        norm = torch.linalg.norm(y - degradation(x_den), dim=1, ord=ps.norm)
+        if fused_params is not None and ps.norm == 2:
+            norm = rec_guidance_norms(x_den, y, self.freqs, fused_params, self.args.tester.blind_bwe.NFFT)
+        else:
+            norm = torch.linalg.norm(y - degradation(x_den), dim=1, ord=ps.norm)
         (g,) = torch.autograd.grad(outputs=norm.sum(), inputs=x_in)
         normguide = torch.linalg.norm(g) / self.args.exp.audio_len ** 0.5
         return self.xi / (normguide + 1e-6) * g / t_in
 
-    def get_score(self, x, y, t_i, degradation, dc_step=None):
+    def get_score(self, x, y, t_i, degradation, dc_step=None, fused_params=None):
         """testing/blind_bwe_sampler.py:160-209.  ``dc_step(x_hat)``: optional data-consistency step."""
         if y is None:
             with torch.no_grad():
@@ -521,7 +643,7 @@ class BlindSamplerFused:
         if self.xi > 0:
             x = x.detach().requires_grad_(True)
             x_den = self.get_denoised_estimate(x, t_i)
-            rec = self._generic_rec_grads(x_den, y, x, t_i, degradation)
+            rec = self._generic_rec_grads(x_den, y, x, t_i, degradation, fused_params)
             x = x.detach()
             score = self.denoised2score(x_den.detach(), x, t_i) - rec
             if dc_step is not None:
@@ -533,7 +655,7 @@ class BlindSamplerFused:
                 x_hat = dc_step(x_hat)
             return self.denoised2score(x_hat, x, t_i)
 
-    def predict_conditional(self, y, degradation, rid=False, dc_step=None):
+    def predict_conditional(self, y, degradation, rid=False, dc_step=None, fused_params=None):
         """testing/blind_bwe_sampler.py:387-497 (``predict`` with observations y)."""
         shape, device = y.shape, y.device
         if self.start_sigma is None:
@@ -549,7 +671,7 @@ class BlindSamplerFused:
             data_score = torch.zeros((self.nb_steps, shape[0], shape[1]))
         for i in range(self.nb_steps):
             x_hat, t_hat = self.move_timestep(x, t[i], gamma[i], self.diff_params.Snoise)
-            score = self.get_score(x_hat, y, t_hat, degradation, dc_step)
+            score = self.get_score(x_hat, y, t_hat, degradation, dc_step, fused_params)
             d = -t_hat * score
             if rid:
                 data_denoised[i] = self.score2denoised(score, x_hat, t_hat)
@@ -558,7 +680,7 @@ class BlindSamplerFused:
             if float(t_host[i + 1]) != 0 and self.order == 2:
                 t_prime = t[i + 1]
                 x_prime = x_hat + h * d
-                score = self.get_score(x_prime, y, t_prime, degradation, dc_step)
+                score = self.get_score(x_prime, y, t_prime, degradation, dc_step, fused_params)
                 x = x_hat + h * ((1 / 2) * d + (1 / 2) * (-t_prime * score))
             else:
                 x = x_hat + h * d
@@ -596,53 +718,29 @@ class BlindSamplerFused:
         return self.predict_conditional(y, degradation, rid, dc_step)
 
     def predict_bwe(self, ylpf, filt, filt_type, rid=False, test_filter_fit=False, compute_sweep=False):
-        """testing/blind_bwe_sampler.py:306-364, the ``fc_A`` branch (known
-        parametric filter, no re-estimation).  The classical FIR/IIR observation
-        models (utils/bandwidth_extension.py) are outside this path."""
+        """testing/blind_bwe_sampler.py:306-364: non-blind bandwidth extension with a KNOWN observation model,
+        routed like the reference through ``predict_conditional`` / ``get_score`` (:160-209, 387-497): with
+        ``rid`` the tuple (x, data_denoised, data_score, t) is returned, ``posterior_sampling.data_consistency``
+        applies the classic data-consistency step and xi == 0 uses the plain denoiser.  ``fc_A`` (parametric filter,
+        fused design + STFT filter guidance) and the FIR models run on the CUDA operators; the IIR / biquad /
+        resampling models and the logging-only ``test_filter_fit`` / ``compute_sweep`` flags raise."""
         if filt_type not in ("fc_A", "firwin", "firwin_hpf"):
             raise NotImplementedError(f"filt_type {filt_type!r}: 'fc_A', 'firwin' and 'firwin_hpf' run on the "
                                       "CUDA operators; the IIR / resampling models are outside this path")
+        if test_filter_fit or compute_sweep:
+            raise NotImplementedError("test_filter_fit / compute_sweep logging on the non-blind path")
         args = self.args
         device = ylpf.device
-        self.freqs = torch.fft.rfftfreq(args.tester.blind_bwe.NFFT, d=1 / args.exp.sample_rate).to(device)
-        params = filt.to(device)
-        fir = filt_type != "fc_A"
-        y = ylpf
-        shape = y.shape
-        if self.start_sigma is None:
-            t = self.diff_params.create_schedule(self.nb_steps).to(device)
-            x = self._randn(shape, device) * t[0]
+        fused = None
+        if filt_type == "fc_A":
+            self.freqs = torch.fft.rfftfreq(args.tester.blind_bwe.NFFT, d=1 / args.exp.sample_rate).to(device)
+            self.params = filt.to(device)
+            degradation = lambda x: self.apply_filter_fcA(x, self.params)
+            fused = self.params
         else:
-            t = self.diff_params.create_schedule_from_initial_t(self.start_sigma, self.nb_steps).to(device)
-            x = y + self._randn(shape, device) * t[0]
-        gamma = self.diff_params.get_gamma(t).to(device)
-        t_host = t.cpu()
-
-        def fir_rec_grads(x_den, x_in, t_in):
-            """get_rec_grads (:75-135, norm 2) with the FIR degradation of apply_FIR_filter (:211-218)."""
-            from . import bandwidth_extension as bwe
-            norm = torch.linalg.norm(y - bwe.apply_low_pass_firwin(x_den, params), dim=1, ord=2)
-            (g,) = torch.autograd.grad(outputs=norm.sum(), inputs=x_in)
-            normguide = torch.linalg.norm(g) / args.exp.audio_len ** 0.5
-            return self.xi / (normguide + 1e-6) * g / t_in
-
-        def score_fn(x_in, t_in):
-            x_in = x_in.detach().requires_grad_(True)
-            x_den = self.get_denoised_estimate(x_in, t_in)
-            rec = fir_rec_grads(x_den, x_in, t_in) if fir else self.get_rec_grads(x_den, y, x_in, t_in, params)
-            x_in = x_in.detach()
-            return (x_den.detach() - x_in) / t_in ** 2 - rec
-
-        for i in range(self.nb_steps):
-            x_hat, t_hat = self.move_timestep(x, t[i], gamma[i], self.diff_params.Snoise)
-            score = score_fn(x_hat, t_hat)
-            d = -t_hat * score
-            h = t[i + 1] - t_hat
-            if float(t_host[i + 1]) != 0 and self.order == 2:
-                t_prime = t[i + 1]
-                x_prime = x_hat + h * d
-                score = score_fn(x_prime, t_prime)
-                x = x_hat + h * ((1 / 2) * d + (1 / 2) * (-t_prime * score))
-            else:
-                x = x_hat + h * d
-        return x.detach()
+            self.filt = filt.to(device)
+            degradation = self.apply_FIR_filter
+        dc_step = None
+        if self.data_consistency:                     # data_consistency_step_classic (:63-73) inside get_score (:182-204)
+            dc_step = lambda x_hat: ylpf + x_hat - degradation(x_hat)
+        return self.predict_conditional(ylpf, degradation, rid, dc_step, fused_params=fused)

@@ -69,6 +69,9 @@ def restore_recording(sampler, degraded, seg_len, ola=256, discard_end=200, join
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     segs, spans = split(degraded, seg_len, ola, discard_end)
+    if world > segs.shape[0]:
+        raise ValueError(f"{world} ranks for {segs.shape[0]} segments: every rank needs at least one segment "
+                         "(an empty shard would enter the NCCL gathers with a different shape)")
     lo, hi = bd.shard_rows(segs.shape[0], rank, world)
     mine = segs[lo:hi]
     if joint:

@@ -280,17 +280,23 @@ def run_ours(a):
     # `value`: device-resident run without per-call CUDA events; a second, identical pass with the
     # events on supplies the per-kernel table of `roofline` (the events cost host time only)
     use_graph = not (a.no_cuda_graph or a.single_pass)      # ncu launch lists profile the eager launches
-    smp.cuda_graph = use_graph
+    # whole-step CUDA graph when it captures; else the denoiser-only graphs; else eager
+    smp.step_graph, smp.cuda_graph = use_graph and not joint and not a.no_step_graph, False
     dev_run, _, _ = timed_run("device")
-    graphed = smp._graphed is not None
-    smp.cuda_graph = False               # the per-kernel pass needs the wrappers to run (eager)
+    graphed = "step" if smp._step_graphs else False
+    if use_graph and not graphed:
+        smp.step_graph, smp.cuda_graph = False, True
+        dev_run, _, _ = timed_run("device")
+        graphed = "denoiser" if smp._graphed is not None else False
+    graph_mode = (smp.step_graph, smp.cuda_graph)
+    smp.step_graph, smp.cuda_graph = False, False      # the per-kernel pass needs the wrappers to run (eager)
     if a.single_pass:                    # ncu launch lists: exactly K timed steps, no second pass
         prof_run = dev_run
     else:
         profiling.enable(True)
         prof_run, _, _ = timed_run("device")
         profiling.enable(False)
-    smp.cuda_graph = use_graph
+    smp.step_graph, smp.cuda_graph = graph_mode
     if a.skip_e2e:                       # profiling runs (ncu) only need the device-resident leg
         e2e_run, h2d, d2h = dev_run, 0, 0
     else:
@@ -699,7 +705,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
     ap.add_argument("--no-cuda-graph", action="store_true",
-                    help="run the denoiser eagerly instead of replaying captured CUDA graphs")
+                    help="run everything eagerly instead of replaying captured CUDA graphs")
+    ap.add_argument("--no-step-graph", action="store_true",
+                    help="capture only the denoiser's forward / backward (round-1 behaviour), not the whole step")
     ap.add_argument("--single-pass", action="store_true",
                     help="profiling aid: skip the second (per-kernel event timing) pass")
     ap.add_argument("--no-autotune", action="store_true", help="profiling aid: cudnn.benchmark off")

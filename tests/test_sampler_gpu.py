@@ -86,6 +86,24 @@ def test_cuda_graph_replay_matches_eager(golden):
     assert rel_l2(x1, x0) < 1e-6 and rel_l2(p1, p0) < 1e-6
 
 
+def test_whole_step_graph_matches_eager(golden):
+    """ONE captured CUDA graph per sampler step (move, denoiser fwd + bwd, statistics, fit loop, fused
+    guidance, Heun correction, state update) replayed with device-resident schedule scalars."""
+    g, y, args, model, s = _setup(golden, max_iter=3)
+    torch.backends.cudnn.deterministic = True
+    torch.manual_seed(5)
+    x0, p0, den0, t0, f0 = s.predict_blind_bwe(y.clone(), rid=True)
+    s.step_graph = True
+    torch.manual_seed(5)
+    x1, p1, den1, t1, f1 = s.predict_blind_bwe(y.clone(), rid=True)
+    assert s._step_graphs, "capture failed"
+    assert rel_l2(x1, x0) < 1e-6 and rel_l2(p1, p0) < 1e-6
+    assert rel_l2(den1, den0) < 1e-6 and rel_l2(f1, f0) < 1e-6
+    torch.manual_seed(5)                                   # replay again from the cached graphs
+    x2, p2 = s.predict_blind_bwe(y.clone())
+    assert rel_l2(x2, x0) < 1e-6 and rel_l2(p2, p0) < 1e-6
+
+
 def test_compute_sweep_matches_oracle(golden):
     """a14 (testing/blind_bwe_sampler.py:598-616): loss and (d/dfc, d/dA) on the 15x12 grid."""
     from oracle import filter_fit as ofit, stft_filter as osf
