@@ -263,6 +263,14 @@ __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int til
       wst[n1 * BAND_THREADS + tid] = w;
       stage[n1 * BAND_THREADS + tid] = make_float2(0.f, 0.f);
     }
+  } else {
+    // synthesis: the dual-window samples of this thread's 16 OUTPUT slots (zero = outside the band's window)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      int i = C::out_slot(r, t) + half;
+      if (i >= M) i -= M;
+      wst[r * BAND_THREADS + tid] = (active && i < lg) ? a.win[off + i] : 0.f;
+    }
   }
   const int row0 = blockIdx.y * a.rows_per_cta;
   const int row_end = min(a.B, (int)(blockIdx.y + 1) * a.rows_per_cta);
@@ -337,7 +345,7 @@ __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int til
           int i = C::out_slot(r, t) + half;
           if (i >= M) i -= M;
           if (i < lg) {
-            const float w = a.win[off + i];
+            const float w = wst[r * BAND_THREADS + tid];
             BS[i] = make_float2(re[r] * w, im[r] * w);
           }
         }
