@@ -21,10 +21,13 @@
 
 namespace babe {
 
-constexpr int TF_THREADS = 256;      // 16 half-warp slots
-constexpr int TF_SEQ = 16;           // sequences per tile
-constexpr int TF_PITCH = 17;         // float2 per element row
+constexpr int TF_THREADS = 256;
 constexpr int TF_TW_LO = 1024;       // low part of the two-level twiddle tables
+// SEQ sequences per tile (16: a half-warp per butterfly, 128-byte global segments, 128 registers -> 2 CTAs per SM;
+// 8: a quarter-warp per butterfly, 64-byte segments, 80 registers -> 3 CTAs per SM), row pitch SEQ + 1 float2
+template <int SEQ> struct TileCfg {
+  static constexpr int PITCH = SEQ + 1, SLOTS = TF_THREADS / SEQ, HALF = SEQ / 2, CTAS = SEQ == 16 ? 2 : 3;
+};
 
 __device__ __forceinline__ float2 tf_tw2(const float2* tab, int m) {
   // exp(-2 pi i m / n) = lo[m & 1023] * hi[m >> 10]
@@ -32,12 +35,13 @@ __device__ __forceinline__ float2 tf_tw2(const float2* tab, int m) {
 }
 
 // One Stockham stage over the tile: radix R, Ns = product of the radices already applied.
-template <int R>
+template <int R, int SEQ>
 __device__ __forceinline__ void tile_stage(const float2* src, float2* dst, int n, int Ns, FastDiv dns,
                                            const float2* roots, int slot, int s) {
+  constexpr int TF_PITCH = TileCfg<SEQ>::PITCH;
   const int m = n / R;
   const int tw_step = m / Ns;
-  for (int j = slot; j < m; j += TF_THREADS / 16) {
+  for (int j = slot; j < m; j += TileCfg<SEQ>::SLOTS) {
     const int k = dns.mod(j);
     float vr[R], vi[R];
     const float2* p = src + j * TF_PITCH + s;
@@ -55,6 +59,7 @@ __device__ __forceinline__ void tile_stage(const float2* src, float2* dst, int n
 }
 
 // Forward FFT of the 16 sequences of a tile; data starts in `a`, returns the buffer holding the result.
+template <int SEQ>
 __device__ __forceinline__ float2* tile_fft(float2* a, float2* b, const FftFactors& f, const float2* roots,
                                             int slot, int s) {
   int Ns = 1;
@@ -63,18 +68,18 @@ __device__ __forceinline__ float2* tile_fft(float2* a, float2* b, const FftFacto
   for (int st = 0; st < f.nf; ++st) {
     const int r = f.radix[st];
     switch (r) {
-      case 2: tile_stage<2>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 3: tile_stage<3>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 4: tile_stage<4>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 5: tile_stage<5>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 7: tile_stage<7>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 8: tile_stage<8>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 11: tile_stage<11>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 13: tile_stage<13>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 16: tile_stage<16>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 17: tile_stage<17>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 19: tile_stage<19>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
-      case 23: tile_stage<23>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 2: tile_stage<2, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 3: tile_stage<3, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 4: tile_stage<4, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 5: tile_stage<5, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 7: tile_stage<7, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 8: tile_stage<8, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 11: tile_stage<11, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 13: tile_stage<13, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 16: tile_stage<16, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 17: tile_stage<17, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 19: tile_stage<19, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
+      case 23: tile_stage<23, SEQ>(src, dst, f.n, Ns, f.div_ns[st], roots, slot, s); break;
       default: break;
     }
     Ns *= r;
@@ -96,23 +101,25 @@ struct F1Args {
   int twiddle, conj_out;
 };
 
-__global__ void __launch_bounds__(TF_THREADS, 2) k_fft_n1(const F1Args a) {
+template <int SEQ>
+__global__ void __launch_bounds__(TF_THREADS, TileCfg<SEQ>::CTAS) k_fft_n1(const F1Args a) {
+  constexpr int TF_PITCH = TileCfg<SEQ>::PITCH, TF_SEQ = SEQ, SLOTS = TileCfg<SEQ>::SLOTS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* A = reinterpret_cast<float2*>(smem_raw);
   float2* Bf = A + a.N1 * TF_PITCH;
   float2* roots = Bf + a.N1 * TF_PITCH;
-  const int tid = threadIdx.x, slot = tid >> 4, s = tid & 15;
+  const int tid = threadIdx.x, slot = tid / SEQ, s = tid % SEQ;
   for (int i = tid; i < a.N1; i += TF_THREADS) roots[i] = a.roots[i];
   const int q = blockIdx.x * TF_SEQ + s;
   const bool live = q < a.N2;
   const float2* in = a.in + (size_t)blockIdx.y * a.Nc;
   float2* out = a.out + (size_t)blockIdx.y * a.Nc;
-  for (int e = slot; e < a.N1; e += TF_THREADS / 16)
+  for (int e = slot; e < a.N1; e += SLOTS)
     A[e * TF_PITCH + s] = live ? in[(size_t)e * a.N2 + q] : make_float2(0.f, 0.f);
   __syncthreads();
-  const float2* res = tile_fft(A, Bf, a.f, roots, slot, s);
+  const float2* res = tile_fft<SEQ>(A, Bf, a.f, roots, slot, s);
   if (!live) return;
-  for (int e = slot; e < a.N1; e += TF_THREADS / 16) {
+  for (int e = slot; e < a.N1; e += SLOTS) {
     float2 v = res[e * TF_PITCH + s];
     if (a.twiddle) v = cmul(v, tf_tw2(a.tw_nc, q * e));
     if (a.conj_out) v.y = -v.y;
@@ -137,15 +144,15 @@ struct F2Args {
   const int* band_p; const int* band_lg; const int* band_off; const int* jlo; const int* jhi;
 };
 
-__device__ __forceinline__ int f2_tiles(int N1) { return ((N1 - 1) / 2 + 7) / 8 + 1; }
-// sequence of slot s in tile t (-1: empty slot)
+// sequence of slot s in tile t (-1: empty slot); H = SEQ / 2 pairs per tile
+template <int H>
 __device__ __forceinline__ int f2_seq(int N1, int tile, int s) {
   const int P = (N1 - 1) / 2;                    // pairs (k1, N1 - k1), k1 = 1..P
-  const int ntp = (P + 7) / 8;
+  const int ntp = (P + H - 1) / H;
   if (tile < ntp) {
-    const int lo = 1 + 8 * tile + (s & 7);
+    const int lo = 1 + H * tile + (s % H);
     if (lo > P) return -1;
-    return s < 8 ? lo : N1 - lo;
+    return s < H ? lo : N1 - lo;
   }
   if (s == 0) return 0;
   if (s == 1 && (N1 & 1) == 0) return N1 / 2;
@@ -153,12 +160,14 @@ __device__ __forceinline__ int f2_seq(int N1, int tile, int s) {
 }
 
 // forward second pass + r2c post-processing:  Y -> X (half spectrum, Nc+1 bins, optional per-bin scale)
-__global__ void __launch_bounds__(TF_THREADS, 2) k_fft_n2_fwd(const F2Args a) {
+template <int SEQ>
+__global__ void __launch_bounds__(TF_THREADS, TileCfg<SEQ>::CTAS) k_fft_n2_fwd(const F2Args a) {
+  constexpr int TF_PITCH = TileCfg<SEQ>::PITCH, TF_SEQ = SEQ, H = TileCfg<SEQ>::HALF;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* A = reinterpret_cast<float2*>(smem_raw);
   float2* Bf = A + a.N2 * TF_PITCH;
   float2* roots = Bf + a.N2 * TF_PITCH;
-  const int tid = threadIdx.x, slot = tid >> 4, s = tid & 15;
+  const int tid = threadIdx.x, slot = tid / SEQ, s = tid % SEQ;
   for (int i = tid; i < a.N2; i += TF_THREADS) roots[i] = a.roots[i];
   const int tile = blockIdx.x;
   const float2* Y = a.Y + (size_t)blockIdx.y * a.Nc;
@@ -166,22 +175,22 @@ __global__ void __launch_bounds__(TF_THREADS, 2) k_fft_n2_fwd(const F2Args a) {
   // rows are contiguous: lanes run along the element index, the tile is written transposed (pitch 17: conflict-free)
 #pragma unroll 4
   for (int sq = 0; sq < TF_SEQ; ++sq) {
-    const int k1 = f2_seq(a.N1, tile, sq);
+    const int k1 = f2_seq<H>(a.N1, tile, sq);
     for (int e = tid; e < a.N2; e += TF_THREADS)
       A[e * TF_PITCH + sq] = k1 >= 0 ? Y[(size_t)k1 * a.N2 + e] : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  const float2* res = tile_fft(A, Bf, a.f, roots, slot, s);
-  const int ntp = ((a.N1 - 1) / 2 + 7) / 8;
+  const float2* res = tile_fft<SEQ>(A, Bf, a.f, roots, slot, s);
+  const int ntp = ((a.N1 - 1) / 2 + H - 1) / H;
   if (tile < ntp) {
-    // pair (slot i, slot i + 8): Z[k1 + N1 k2] with Z[(N1 - k1) + N1 (N2 - 1 - k2)] = Z[Nc - k]
-    for (int idx = tid; idx < 8 * a.N2; idx += TF_THREADS) {
-      const int i = idx & 7, k2 = idx >> 3;
-      const int k1 = f2_seq(a.N1, tile, i);
+    // pair (slot i, slot i + H): Z[k1 + N1 k2] with Z[(N1 - k1) + N1 (N2 - 1 - k2)] = Z[Nc - k]
+    for (int idx = tid; idx < H * a.N2; idx += TF_THREADS) {
+      const int i = idx % H, k2 = idx / H;
+      const int k1 = f2_seq<H>(a.N1, tile, i);
       if (k1 < 0) continue;
       const int k = k1 + a.N1 * k2, kp = a.Nc - k;
       float2 Xk, Xkp;
-      post_pair(res[k2 * TF_PITCH + i], res[(a.N2 - 1 - k2) * TF_PITCH + i + 8], tf_tw2(a.tw_ls, k), Xk, Xkp);
+      post_pair(res[k2 * TF_PITCH + i], res[(a.N2 - 1 - k2) * TF_PITCH + i + H], tf_tw2(a.tw_ls, k), Xk, Xkp);
       if (a.scale) { const float sk = a.scale[k], sp = a.scale[kp]; Xk.x *= sk; Xk.y *= sk; Xkp.x *= sp; Xkp.y *= sp; }
       X[k] = Xk;
       X[kp] = Xkp;
@@ -246,34 +255,35 @@ __device__ __forceinline__ float2 f2_bin(const F2Args& a, const float2* src, int
 
 // inverse first pass: c2r pre-processing of the bin pairs in the prologue (from X or gathered from the band
 // spectra), FFT_{N2} over k2, twiddle W_Nc^{k1 m1}  ->  Yout[k1 * N2 + m1]
-template <bool GATHER>
-__global__ void __launch_bounds__(TF_THREADS, 2) k_fft_n2_inv(const F2Args a) {
+template <bool GATHER, int SEQ>
+__global__ void __launch_bounds__(TF_THREADS, TileCfg<SEQ>::CTAS) k_fft_n2_inv(const F2Args a) {
+  constexpr int TF_PITCH = TileCfg<SEQ>::PITCH, TF_SEQ = SEQ, H = TileCfg<SEQ>::HALF;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* A = reinterpret_cast<float2*>(smem_raw);
   float2* Bf = A + a.N2 * TF_PITCH;
   float2* roots = Bf + a.N2 * TF_PITCH;
-  const int tid = threadIdx.x, slot = tid >> 4, s = tid & 15;
+  const int tid = threadIdx.x, slot = tid / SEQ, s = tid % SEQ;
   for (int i = tid; i < a.N2; i += TF_THREADS) roots[i] = a.roots[i];
   const int tile = blockIdx.x;
   const float2* src = GATHER ? a.BS + (size_t)blockIdx.y * a.sum_lg : a.X + (size_t)blockIdx.y * (a.Nc + 1);
   float2* Y = a.Yout + (size_t)blockIdx.y * a.Nc;
   const float inv_nc = 1.0f / (float)a.Nc;
-  const int ntp = ((a.N1 - 1) / 2 + 7) / 8;
+  const int ntp = ((a.N1 - 1) / 2 + H - 1) / H;
   if (tile < ntp) {
-    for (int idx = tid; idx < 8 * a.N2; idx += TF_THREADS) {
-      const int i = idx & 7, k2 = idx >> 3;
-      const int k1 = f2_seq(a.N1, tile, i);
+    for (int idx = tid; idx < H * a.N2; idx += TF_THREADS) {
+      const int i = idx % H, k2 = idx / H;
+      const int k1 = f2_seq<H>(a.N1, tile, i);
       float2 Zk = make_float2(0.f, 0.f), Zkp = Zk;
       if (k1 >= 0) {
         const int k = k1 + a.N1 * k2;
         pre_pair(f2_bin<GATHER>(a, src, k), f2_bin<GATHER>(a, src, a.Nc - k), tf_tw2(a.tw_ls, k), inv_nc, Zk, Zkp);
       }
       A[k2 * TF_PITCH + i] = Zk;
-      A[(a.N2 - 1 - k2) * TF_PITCH + i + 8] = Zkp;
+      A[(a.N2 - 1 - k2) * TF_PITCH + i + H] = Zkp;
     }
   } else {
     for (int idx = tid; idx < TF_SEQ * a.N2; idx += TF_THREADS)       // empty slots
-      if ((idx & 15) >= 2 || ((idx & 15) == 1 && (a.N1 & 1))) A[(idx >> 4) * TF_PITCH + (idx & 15)] = make_float2(0.f, 0.f);
+      if ((idx % SEQ) >= 2 || ((idx % SEQ) == 1 && (a.N1 & 1))) A[(idx / SEQ) * TF_PITCH + (idx % SEQ)] = make_float2(0.f, 0.f);
     for (int idx = tid; idx < 2 * a.N2; idx += TF_THREADS) {
       const int which = idx & 1, k2 = idx >> 1;
       if (which == 0) {
@@ -298,17 +308,17 @@ __global__ void __launch_bounds__(TF_THREADS, 2) k_fft_n2_inv(const F2Args a) {
     }
   }
   __syncthreads();
-  const float2* res = tile_fft(A, Bf, a.f, roots, slot, s);
+  const float2* res = tile_fft<SEQ>(A, Bf, a.f, roots, slot, s);
   // rows of Yout are contiguous: lanes along the element index
 #pragma unroll 4
   for (int sq = 0; sq < TF_SEQ; ++sq) {
-    const int k1 = f2_seq(a.N1, tile, sq);
+    const int k1 = f2_seq<H>(a.N1, tile, sq);
     if (k1 < 0) continue;
     for (int e = tid; e < a.N2; e += TF_THREADS)
       Y[(size_t)k1 * a.N2 + e] = cmul(res[e * TF_PITCH + sq], tf_tw2(a.tw_nc, k1 * e));
   }
 }
 
-static inline size_t tile_fft_smem(int n) { return sizeof(float2) * ((size_t)2 * n * TF_PITCH + n); }
+static inline size_t tile_fft_smem(int n, int seq = 16) { return sizeof(float2) * ((size_t)2 * n * (seq + 1) + n); }
 
 }  // namespace babe

@@ -627,9 +627,15 @@ static int launch_f1(const babe_cqt_plan* p, const float2* in, float2* out, int 
   a.f = to_dev(p->f1); a.roots = reinterpret_cast<const float2*>(p->roots1);
   a.tw_nc = reinterpret_cast<const float2*>(p->tw_nc);
   a.twiddle = twiddle; a.conj_out = conj_out;
-  const size_t smem = tile_fft_smem(a.N1);
-  cudaFuncSetAttribute(k_fft_n1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_fft_n1<<<dim3((a.N2 + TF_SEQ - 1) / TF_SEQ, B), TF_THREADS, smem, st>>>(a);
+  if (g_cqt_variant == 1) {
+    const size_t smem = tile_fft_smem(a.N1, 8);
+    cudaFuncSetAttribute(k_fft_n1<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fft_n1<8><<<dim3((a.N2 + 7) / 8, B), TF_THREADS, smem, st>>>(a);
+  } else {
+    const size_t smem = tile_fft_smem(a.N1, 16);
+    cudaFuncSetAttribute(k_fft_n1<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fft_n1<16><<<dim3((a.N2 + 15) / 16, B), TF_THREADS, smem, st>>>(a);
+  }
   return check_launch("k_fft_n1");
 }
 
@@ -642,16 +648,22 @@ static F2Args f2_args(const babe_cqt_plan* p, const float* scale) {
   a.scale = scale;
   return a;
 }
-static int f2_grid(int N1) { return ((N1 - 1) / 2 + 7) / 8 + 1; }
+static int f2_grid(int N1, int half) { return ((N1 - 1) / 2 + half - 1) / half + 1; }
 
 // Y[N1][N2] -> half spectrum X[Nc+1] (times scale)
 static int launch_f2_fwd(const babe_cqt_plan* p, const float2* Y, float2* X, const float* scale, int B,
                          cudaStream_t st) {
   F2Args a = f2_args(p, scale);
   a.Y = Y; a.Xout = X;
-  const size_t smem = tile_fft_smem(a.N2);
-  cudaFuncSetAttribute(k_fft_n2_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_fft_n2_fwd<<<dim3(f2_grid(a.N1), B), TF_THREADS, smem, st>>>(a);
+  if (g_cqt_variant == 1) {
+    const size_t smem = tile_fft_smem(a.N2, 8);
+    cudaFuncSetAttribute(k_fft_n2_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fft_n2_fwd<8><<<dim3(f2_grid(a.N1, 4), B), TF_THREADS, smem, st>>>(a);
+  } else {
+    const size_t smem = tile_fft_smem(a.N2, 16);
+    cudaFuncSetAttribute(k_fft_n2_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fft_n2_fwd<16><<<dim3(f2_grid(a.N1, 8), B), TF_THREADS, smem, st>>>(a);
+  }
   return check_launch("k_fft_n2_fwd");
 }
 
@@ -660,16 +672,21 @@ static int launch_f2_inv(const babe_cqt_plan* p, const float2* X, const float2* 
                          int B, cudaStream_t st) {
   F2Args a = f2_args(p, scale);
   a.X = X; a.Yout = Y;
-  const size_t smem = tile_fft_smem(a.N2);
+  const bool s8 = g_cqt_variant == 1;
+  const size_t smem = tile_fft_smem(a.N2, s8 ? 8 : 16);
+  const dim3 grid(f2_grid(a.N1, s8 ? 4 : 8), B);
   if (BS != nullptr) {
     a.BS = BS; a.sum_lg = p->sum_lg;
     a.band_p = p->band_p; a.band_lg = p->band_lg; a.band_off = p->band_off; a.jlo = p->bin_jlo; a.jhi = p->bin_jhi;
-    cudaFuncSetAttribute(k_fft_n2_inv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fft_n2_inv<true><<<dim3(f2_grid(a.N1), B), TF_THREADS, smem, st>>>(a);
-  } else {
-    cudaFuncSetAttribute(k_fft_n2_inv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fft_n2_inv<false><<<dim3(f2_grid(a.N1), B), TF_THREADS, smem, st>>>(a);
   }
+#define BABE_LAUNCH_INV(G, S)                                                                          \
+  do {                                                                                                 \
+    cudaFuncSetAttribute(k_fft_n2_inv<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    k_fft_n2_inv<G, S><<<grid, TF_THREADS, smem, st>>>(a);                                             \
+  } while (0)
+  if (BS != nullptr) { if (s8) BABE_LAUNCH_INV(true, 8); else BABE_LAUNCH_INV(true, 16); }
+  else { if (s8) BABE_LAUNCH_INV(false, 8); else BABE_LAUNCH_INV(false, 16); }
+#undef BABE_LAUNCH_INV
   return check_launch("k_fft_n2_inv");
 }
 
@@ -881,7 +898,7 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
 
 // profiling / A-B knob (profiles/probe_r02.py): which implementation computes the length-Ls transform
 extern "C" int babe_set_cqt_variant(int v) {
-  if (v < -1 || v > 0) return BABE_EBADARG;
+  if (v < -1 || v > 1) return BABE_EBADARG;
   babe::g_cqt_variant = v;
   return BABE_OK;
 }

@@ -127,7 +127,7 @@ def time_cqt():
     SRc, L = 22050, 184184
     cq = CQT_nsgt(7, 64, mode="oct", window=("kaiser", 1), fs=SRc, audio_len=L, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for B, variant in ((64, -1), (64, 0), (8, -1), (8, 0)):
+    for B, variant in ((64, -1), (64, 0), (64, 1), (8, -1), (8, 0), (8, 1)):
         lib().babe_set_cqt_variant(variant)
         xc = torch.randn(B, L, device=dev) * 0.063
         cs = cq.fwd(xc.unsqueeze(1))

@@ -135,3 +135,30 @@ def test_planar_layout_matches_interleaved(CQT):
     gca = torch.autograd.grad((cq.bwd(ca).squeeze(1) * r).sum(), ca)
     for gp, gc in zip(gpa, gca):
         assert rel_l2(gp.cpu(), torch.view_as_real(gc.squeeze(1)).permute(0, 3, 1, 2).cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("numocts,binsoct,fs,Ls,B", [(4, 12, 22050, 8192, 3), (7, 64, 22050, 184184, 2),
+                                                     (7, 64, 22050, 132300, 1), (8, 96, 44100, 485100, 1)])
+def test_tiled_passes_vs_oracle(CQT, variant, numocts, binsoct, fs, Ls, B):
+    """The alternative length-Ls transform (csrc/cqt_fft.cuh: tiles of 16 / 8 sequences, r2c post-, c2r pre-processing
+    and the synthesis gather fused into the passes; `babe_set_cqt_variant`) against the same oracle."""
+    from babe_b200._lib import lib
+    cq, ref = _pair(CQT, numocts, binsoct, fs, Ls)
+    g = torch.Generator().manual_seed(Ls + 1)
+    x = torch.randn(B, Ls, generator=g) * 0.063
+    xc = x.cuda()
+    assert lib().babe_set_cqt_variant(variant) == 0
+    try:
+        X = cq.rfft(xc)
+        Xr = torch.fft.rfft(x.double(), dim=-1)
+        assert rel_l2(torch.view_as_real(X.cpu()), torch.view_as_real(Xr)) < TOL
+        assert rel_l2(cq.irfft(Xr.to(torch.complex64).cuda()).cpu(), x) < TOL
+        c = cq.fwd(xc.unsqueeze(1))
+        cr = ref.fwd(x.double())
+        for o in range(numocts):
+            assert rel_l2(torch.view_as_real(c[o].cpu().squeeze(1)), torch.view_as_real(cr[o])) < TOL, o
+        assert rel_l2(cq.bwd(c).cpu().squeeze(1), ref.bwd(cr)) < TOL
+        assert rel_l2(cq.apply_hpf_DC(xc).cpu(), ref.apply_hpf_DC(x.double())) < TOL
+    finally:
+        lib().babe_set_cqt_variant(-1)
