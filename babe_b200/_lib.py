@@ -42,7 +42,7 @@ class CqtPlan(ctypes.Structure):
                 ("numocts", c_int), ("binsoct", c_int), ("M", c_int * MAX_OCTAVES),
                 ("fm", FftFactors * MAX_OCTAVES), ("rootsm", c_void_p * MAX_OCTAVES),
                 ("band_p", c_void_p), ("band_lg", c_void_p), ("band_off", c_void_p),
-                ("sum_lg", c_int), ("bin_jlo", c_void_p), ("bin_jhi", c_void_p)]
+                ("sum_lg", c_int), ("bin_jlo", c_void_p), ("bin_jhi", c_void_p), ("bin_src", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/babe_b200.h declares

@@ -145,6 +145,19 @@ class _Geometry:
         k = np.arange(Nc + 1)
         self.jlo = np.searchsorted(end, k, side="right").astype(np.int32)       # first j with end_j > k
         self.jhi = (np.searchsorted(start, k, side="right") - 1).astype(np.int32)  # last j with start_j <= k
+        # per-bin sources of the synthesis overlap-add: offsets into one row of band spectra, <= 4 bands per bin
+        cover = int((self.jhi - self.jlo + 1).max())
+        self.bin_src = None
+        if cover <= 4:
+            src = np.full((Nc + 1, 4), -1, dtype=np.int32)
+            for s in range(cover):
+                j = self.jlo.astype(np.int64) + s
+                ok = j <= self.jhi
+                jj = np.where(ok, j, 0)
+                i = k - start[jj]
+                ok &= (i >= 0) & (i < lg[jj])
+                src[ok, s] = (self.off[jj] + i)[ok]
+            self.bin_src = src
 
 
 class _Plan:
@@ -171,6 +184,7 @@ class _Plan:
         plan.band_off = dev(geo.off.astype(np.int32))
         plan.sum_lg = geo.sum_lg
         plan.bin_jlo, plan.bin_jhi = dev(geo.jlo), dev(geo.jhi)
+        plan.bin_src = dev(geo.bin_src) if geo.bin_src is not None else None
         self.c = plan
         self.n1, self.n2 = n1, n2
         self.coef_per_row = int(binsoct * sum(geo.M))

@@ -22,6 +22,7 @@
 #include "smemfft.cuh"
 #include "rfft_pairs.cuh"
 #include "cqt_fft.cuh"
+#include "cqt_pfa.cuh"
 
 namespace babe {
 
@@ -572,8 +573,11 @@ struct Workspace {
   float2 *bufA, *bufB, *bufX, *bufS;
 };
 
+// per-row elements of the two pass buffers: the prime-factor intermediate pads its rows to an even pitch
+static size_t pass_row(const babe_cqt_plan* p) { return ((size_t)p->Nc + p->f1.n + 8) & ~(size_t)7; }
 static size_t ws_bytes(const babe_cqt_plan* p, int B) {
-  return sizeof(float2) * (size_t)B * ((size_t)2 * p->Nc + (p->Nc + 1) + (size_t)std::max(p->sum_lg, 0)) + 256;
+  return sizeof(float2) * (size_t)B * (2 * pass_row(p) + (((size_t)p->Nc + 8) & ~(size_t)7) +
+                                       (size_t)std::max(p->sum_lg, 0)) + 256;
 }
 
 static int carve(const babe_cqt_plan* p, int B, void* ws, size_t bytes, Workspace& w) {
@@ -581,9 +585,9 @@ static int carve(const babe_cqt_plan* p, int B, void* ws, size_t bytes, Workspac
   BABE_REQUIRE(ws != nullptr && bytes >= ws_bytes(p, B), BABE_EBADARG, "workspace too small (%zu < %zu)",
                bytes, ws_bytes(p, B));
   w.bufA = static_cast<float2*>(ws);
-  w.bufB = w.bufA + (size_t)B * p->Nc;
-  w.bufX = w.bufB + (size_t)B * p->Nc;
-  w.bufS = w.bufX + (size_t)B * (p->Nc + 1);
+  w.bufB = w.bufA + (size_t)B * pass_row(p);
+  w.bufX = w.bufB + (size_t)B * pass_row(p);
+  w.bufS = w.bufX + (size_t)B * (((size_t)p->Nc + 8) & ~(size_t)7);
   return BABE_OK;
 }
 
@@ -615,9 +619,102 @@ static int big_fft(const babe_cqt_plan* p, const float2* in, float2* tmp, float2
 // r02_cqt.md): the tiled passes need 128 registers for the radix-13 / 23 butterflies (2 CTAs per SM) and come out
 // 7-40 % SLOWER than the round-1 passes (80 registers, 3 CTAs per SM) despite two launches fewer, so round 1's are
 // the default.
-static int g_cqt_variant = -1;
+//  2 (default): prime-factor passes (cqt_pfa.cuh) for the instantiated lengths, round-1 passes otherwise.
+static int g_cqt_variant = 2;
 static bool tiled_ok(const babe_cqt_plan* p) {
-  return g_cqt_variant >= 0 && tile_fft_smem(p->f1.n) <= 220 * 1024 && tile_fft_smem(p->f2.n) <= 220 * 1024;
+  return (g_cqt_variant == 0 || g_cqt_variant == 1) && tile_fft_smem(p->f1.n) <= 220 * 1024 &&
+         tile_fft_smem(p->f2.n) <= 220 * 1024;
+}
+
+// ---- third-generation length-Ls transform: prime-factor passes (cqt_pfa.cuh) -----------------------------------
+using Pfa92092 = pfa::Plan<4, 7, 11, 13, 23, 1>;      // Ls = 184184: 22.05 kHz x 8.35 s (BASELINE configs[1])
+using Pfa184184 = pfa::Plan<8, 7, 11, 13, 23, 1>;     // Ls = 368368: 44.1 kHz x 8.35 s (conf/exp/maestro44k_8s.yaml)
+constexpr int PFA_S = 16;
+
+static int pfa_id(const babe_cqt_plan* p) {
+  if (g_cqt_variant != 2) return 0;
+  if (p->Nc == Pfa92092::NC) return 1;
+  if (p->Nc == Pfa184184::NC) return 2;
+  return 0;
+}
+
+template <class PL>
+struct PfaRun {
+  using P1 = pfa::Pass1<PL, PFA_S>;
+  using P2 = pfa::Pass2<PL, PFA_S>;
+  static int pass1_fwd(const float2* x, float2* Y, int B, cudaStream_t st) {
+    cudaFuncSetAttribute(pfa::k_pfa1_fwd<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1::SMEM);
+    pfa::k_pfa1_fwd<PL, PFA_S><<<dim3(P1::TILES, B), pfa::THREADS, P1::SMEM, st>>>(x, Y);
+    return check_launch("k_pfa1_fwd");
+  }
+  static int pass1_inv(const float2* Y, float2* x, int B, cudaStream_t st) {
+    cudaFuncSetAttribute(pfa::k_pfa1_inv<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1::SMEM);
+    pfa::k_pfa1_inv<PL, PFA_S><<<dim3(P1::TILES, B), pfa::THREADS, P1::SMEM, st>>>(Y, x);
+    return check_launch("k_pfa1_inv");
+  }
+  static pfa::P2Args args(const babe_cqt_plan* p, const float* scale) {
+    pfa::P2Args a{};
+    a.tw_ls = reinterpret_cast<const float2*>(p->tw_ls);
+    a.scale = scale;
+    return a;
+  }
+  // x[B, Ls] -> X[B, Nc + 1] * scale
+  static int rfft(const babe_cqt_plan* p, const float2* x, float2* tmp, float2* X, const float* scale, int B,
+                  cudaStream_t st) {
+    int rc = pass1_fwd(x, tmp, B, st);
+    if (rc) return rc;
+    pfa::P2Args a = args(p, scale);
+    a.Y = tmp; a.Xout = X;
+    cudaFuncSetAttribute(pfa::k_pfa2_fwd<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
+    pfa::k_pfa2_fwd<PL, PFA_S><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
+    return check_launch("k_pfa2_fwd");
+  }
+  // X[B, Nc + 1] * scale (or the gathered band spectra) -> x[B, Ls]
+  static int irfft(const babe_cqt_plan* p, const float2* X, const float2* BS, float2* tmp, float2* x,
+                   const float* scale, int B, cudaStream_t st) {
+    pfa::P2Args a = args(p, scale);
+    a.X = X; a.Yout = tmp;
+    if (BS != nullptr) {
+      a.BS = BS; a.src = reinterpret_cast<const int4*>(p->bin_src); a.sum_lg = p->sum_lg;
+      cudaFuncSetAttribute(pfa::k_pfa2_inv<PL, PFA_S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
+      pfa::k_pfa2_inv<PL, PFA_S, true><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
+    } else {
+      cudaFuncSetAttribute(pfa::k_pfa2_inv<PL, PFA_S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
+      pfa::k_pfa2_inv<PL, PFA_S, false><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
+    }
+    int rc = check_launch("k_pfa2_inv");
+    if (rc) return rc;
+    return pass1_inv(tmp, x, B, st);
+  }
+  // y = irfft(rfft(x) H): three launches, the spectrum never leaves shared memory
+  static int filter(const babe_cqt_plan* p, const float2* x, float2* tmpA, float2* tmpB, float2* y, const float* H,
+                    int B, cudaStream_t st) {
+    int rc = pass1_fwd(x, tmpA, B, st);
+    if (rc) return rc;
+    pfa::P2Args a = args(p, H);
+    a.Y = tmpA; a.Yout = tmpB;
+    cudaFuncSetAttribute(pfa::k_pfa2_mid<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
+    pfa::k_pfa2_mid<PL, PFA_S><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
+    rc = check_launch("k_pfa2_mid");
+    if (rc) return rc;
+    return pass1_inv(tmpB, y, B, st);
+  }
+};
+
+static int pfa_rfft(const babe_cqt_plan* p, const float2* x, float2* tmp, float2* X, const float* scale, int B,
+                    cudaStream_t st) {
+  return pfa_id(p) == 1 ? PfaRun<Pfa92092>::rfft(p, x, tmp, X, scale, B, st)
+                        : PfaRun<Pfa184184>::rfft(p, x, tmp, X, scale, B, st);
+}
+static int pfa_irfft(const babe_cqt_plan* p, const float2* X, const float2* BS, float2* tmp, float2* x,
+                     const float* scale, int B, cudaStream_t st) {
+  return pfa_id(p) == 1 ? PfaRun<Pfa92092>::irfft(p, X, BS, tmp, x, scale, B, st)
+                        : PfaRun<Pfa184184>::irfft(p, X, BS, tmp, x, scale, B, st);
+}
+static int pfa_filter(const babe_cqt_plan* p, const float2* x, float2* tmpA, float2* tmpB, float2* y,
+                      const float* H, int B, cudaStream_t st) {
+  return pfa_id(p) == 1 ? PfaRun<Pfa92092>::filter(p, x, tmpA, tmpB, y, H, B, st)
+                        : PfaRun<Pfa184184>::filter(p, x, tmpA, tmpB, y, H, B, st);
 }
 
 static int launch_f1(const babe_cqt_plan* p, const float2* in, float2* out, int B, int twiddle, int conj_out,
@@ -761,6 +858,8 @@ extern "C" int babe_rfft(const babe_cqt_plan* plan, const float* x, float* X, in
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pfa_id(plan))
+    return pfa_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, reinterpret_cast<float2*>(X), bin_scale, B, st);
   if (tiled_ok(plan))
     return tiled_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, reinterpret_cast<float2*>(X), bin_scale, B, st);
   rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
@@ -782,6 +881,9 @@ extern "C" int babe_irfft(const babe_cqt_plan* plan, const float* X, float* x, i
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pfa_id(plan))
+    return pfa_irfft(plan, reinterpret_cast<const float2*>(X), nullptr, w.bufA, reinterpret_cast<float2*>(x),
+                     bin_scale, B, st);
   if (tiled_ok(plan))
     return tiled_irfft(plan, reinterpret_cast<const float2*>(X), nullptr, w.bufA, reinterpret_cast<float2*>(x),
                        bin_scale, B, st);
@@ -805,6 +907,8 @@ extern "C" int babe_spectral_filter(const babe_cqt_plan* plan, const float* x, f
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pfa_id(plan))
+    return pfa_filter(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, reinterpret_cast<float2*>(y), H, B, st);
   if (tiled_ok(plan)) {
     rc = tiled_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufX, H, B, st);
     if (rc) return rc;
@@ -831,7 +935,10 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tiled_ok(plan)) {
+  if (pfa_id(plan)) {
+    rc = pfa_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufX, nullptr, B, st);
+    if (rc) return rc;
+  } else if (tiled_ok(plan)) {
     rc = tiled_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufX, nullptr, B, st);
     if (rc) return rc;
   } else {
@@ -882,6 +989,8 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
   k_cqt_synth_bands<<<dim3(items, (B + a.rows_per_cta - 1) / a.rows_per_cta), BAND_THREADS, smem, st>>>(a);
   rc = check_launch("k_cqt_synth_bands");
   if (rc) return rc;
+  if (pfa_id(plan) && plan->bin_src != nullptr)   // table-driven overlap-add gather in the prologue of the inverse pass 2
+    return pfa_irfft(plan, nullptr, w.bufS, w.bufA, reinterpret_cast<float2*>(x), bin_scale, B, st);
   if (tiled_ok(plan))       // overlap-add gather + c2r pre-processing in the prologue of the inverse's first pass
     return tiled_irfft(plan, nullptr, w.bufS, w.bufA, reinterpret_cast<float2*>(x), bin_scale, B, st);
   GatherArgs g{};
@@ -898,7 +1007,7 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
 
 // profiling / A-B knob (profiles/probe_r02.py): which implementation computes the length-Ls transform
 extern "C" int babe_set_cqt_variant(int v) {
-  if (v < -1 || v > 1) return BABE_EBADARG;
+  if (v < -1 || v > 2) return BABE_EBADARG;
   babe::g_cqt_variant = v;
   return BABE_OK;
 }

@@ -1,0 +1,444 @@
+// Third-generation length-Ls transform of the CQT: a PRIME-FACTOR (Good-Thomas) FFT in two passes.
+//
+// Ls = 184184 = 2 * (4 * 7 * 11) * (13 * 23): all factors of Nc = Ls / 2 are pairwise coprime, so the complex FFT of
+// Nc points is a five-dimensional DFT with NO twiddle factors between any two stages:
+//
+//     n = sum_i n_i * (Nc / R_i)  (mod Nc)      input index  (Ruritanian map; n_i = ((n mod R_i) * inv_i) mod R_i)
+//     k = k_i  (mod R_i)                        output index (Chinese remainder map)
+//     W_Nc^{n k} = prod_i W_{R_i}^{n_i k_i}
+//
+// Pass 1 transforms the digits of N1 = RA*RB*RC for a tile of S consecutive residues r = n mod N2 (the elements
+// n = r + N2 j of S neighbouring residues are S consecutive complex samples: 128-byte runs), pass 2 the digits of
+// N2 = RD*RE*RF for the S rows of S/2 residue pairs (k1, N1 - k1) of k mod N1 -- both members of every bin pair
+// (k, Nc - k) of the real-FFT post-processing sit in the same tile, and the bins k = k1 + N1 j of consecutive k1 are
+// consecutive in the natural-order half spectrum (64-byte runs).  A tile lives in shared memory as [digit index][S]
+// float2 and every stage works IN PLACE with compile-time strides (one buffer, no twiddle tables, no Stockham index
+// arithmetic); the input / output permutations are two small tables built by every CTA.  The odd-prime DFTs keep the
+// (R-1)/2 sums and differences of the mirrored inputs in registers and store every output pair as soon as it is
+// complete, which fits the radix-23 butterfly into 64 registers (round 2's tiled passes kept all R outputs: 128).
+//
+// apply_hpf_DC needs 3 launches instead of 5 (pass 2 runs forward, multiplies by H in the r2c / c2r pair processing
+// and runs backward without leaving shared memory), analysis 2 + 1, synthesis 1 + 2 (the overlap-add of the band
+// spectra is a table-driven gather in the prologue of the inverse pass 2).
+//
+// All per-thread phases are __host__ __device__: tests/host/pfa_host_check.cu emulates the kernels thread by thread
+// against numpy.  Lengths whose factorisation is not instantiated keep the generic passes of cqt_ops.cu.
+#pragma once
+#include "rfft_pairs.cuh"
+
+namespace babe {
+namespace pfa {
+
+constexpr int THREADS = 256;
+constexpr int TW_LO_ = 1024;
+
+BABE_HD constexpr int modinv(int a, int m) {
+  a %= m;
+  for (int x = 1; x < m; ++x)
+    if ((a * x) % m == 1) return x;
+  return 0;
+}
+
+template <int RA_, int RB_, int RC_, int RD_, int RE_, int RF_>
+struct Plan {
+  static constexpr int RA = RA_, RB = RB_, RC = RC_, RD = RD_, RE = RE_, RF = RF_;
+  static constexpr int N1 = RA * RB * RC, N2 = RD * RE * RF, NC = N1 * N2;
+  static constexpr int P2 = (N2 + 1) & ~1;          // row pitch of the intermediate in float2 (even: 16-byte rows)
+  static constexpr int IA = modinv((NC / RA) % RA, RA), IB = modinv((NC / RB) % RB, RB), IC = modinv((NC / RC) % RC, RC);
+  static constexpr int ID = modinv((NC / RD) % RD, RD), IE = modinv((NC / RE) % RE, RE), IF_ = modinv((NC / RF) % RF, RF);
+  // input side: digit index of residue m = n mod N1 (pass 1) / r = n mod N2 (pass 2)
+  BABE_HD static int t1(int m) { return (((m % RA) * IA % RA) * RB + ((m % RB) * IB % RB)) * RC + ((m % RC) * IC % RC); }
+  BABE_HD static int t2(int r) { return (((r % RD) * ID % RD) * RE + ((r % RE) * IE % RE)) * RF + ((r % RF) * IF_ % RF); }
+  // output side: digit index of k1 = k mod N1 / r2 = k mod N2
+  BABE_HD static int q1(int k1) { return ((k1 % RA) * RB + k1 % RB) * RC + k1 % RC; }
+  BABE_HD static int d2(int r2) { return ((r2 % RD) * RE + r2 % RE) * RF + r2 % RF; }
+};
+
+// exp(-2 pi i m / Ls) from the plan's two-level table
+BABE_HD float2 tw_ls(const float2* tab, int m) { return cmul(tab[m & (TW_LO_ - 1)], tab[TW_LO_ + (m >> 10)]); }
+
+// In-place DFT of the R points p[0], p[st], ..., p[(R-1) st]; INV: conjugated roots (no scaling).
+template <int R, bool INV>
+BABE_HD void dft_inplace(float2* p, const int st) {
+  if constexpr (R == 1) {
+    return;
+  } else if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
+    float re[R], im[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) { const float2 v = p[t * st]; re[t] = v.x; im[t] = v.y; }
+    if (INV) butterfly<R>(im, re, nullptr, 0); else butterfly<R>(re, im, nullptr, 0);
+#pragma unroll
+    for (int t = 0; t < R; ++t) p[t * st] = make_float2(re[t], im[t]);
+  } else {
+    // odd prime: a_t = v_t + v_{R-t}, b_t = v_t - v_{R-t};  X_u = v_0 + sum a_t cos - i sum b_t sin, X_{R-u} with + i
+    constexpr int H = (R - 1) / 2;
+    const float2 x0 = p[0];
+    float ar[H], ai[H], br[H], bi[H];
+    float s0r = x0.x, s0i = x0.y;
+#pragma unroll
+    for (int t = 1; t <= H; ++t) {
+      const float2 u = p[t * st], v = p[(R - t) * st];
+      ar[t - 1] = u.x + v.x; ai[t - 1] = u.y + v.y;
+      br[t - 1] = u.x - v.x; bi[t - 1] = u.y - v.y;
+      s0r += ar[t - 1]; s0i += ai[t - 1];
+    }
+    p[0] = make_float2(s0r, s0i);
+#pragma unroll
+    for (int u = 1; u <= H; ++u) {
+      float Ar = x0.x, Ai = x0.y, Br = 0.f, Bi = 0.f;
+#pragma unroll
+      for (int t = 1; t <= H; ++t) {
+        const int m = (t * u) % R;
+        const float c = odd_cos<R>(m), sn = odd_sin<R>(m);
+        Ar = fmaf(ar[t - 1], c, Ar); Ai = fmaf(ai[t - 1], c, Ai);
+        Br = fmaf(br[t - 1], sn, Br); Bi = fmaf(bi[t - 1], sn, Bi);
+      }
+      const float2 lo = make_float2(Ar + Bi, Ai - Br), hi = make_float2(Ar - Bi, Ai + Br);   // A - iB, A + iB
+      p[u * st] = INV ? hi : lo;
+      p[(R - u) * st] = INV ? lo : hi;
+    }
+  }
+}
+
+// One stage: digit of radix R with CO digit combinations above it and CI below; element (o, d, i) at ((o R + d) CI + i) S.
+template <int R, int CO, int CI, int S, bool INV>
+BABE_HD void stage(float2* A, int slot, int col, int nslots) {
+  if constexpr (R > 1) {
+    constexpr int NB = CO * CI;
+#pragma unroll 1
+    for (int idx = slot; idx < NB; idx += nslots) {
+      const int o = idx / CI, in = idx - o * CI;
+      dft_inplace<R, INV>(A + ((o * R) * CI + in) * S + col, CI * S);
+    }
+  }
+}
+
+#ifdef __CUDA_ARCH__
+#define PFA_SYNC() __syncthreads()
+#else
+#define PFA_SYNC() ((void)0)
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 1: digits of N1 for a tile of S residues r = n mod N2
+// ---------------------------------------------------------------------------------------------------------------------
+template <class PL, int S>
+struct Pass1 {
+  static constexpr int SLOTS = THREADS / S, TILES = (PL::N2 + S - 1) / S;
+  static constexpr size_t SMEM = sizeof(float2) * PL::N1 * S + sizeof(unsigned short) * ((PL::N1 + 7) & ~7);
+  BABE_HD static unsigned short* table(float2* A) { return reinterpret_cast<unsigned short*>(A + PL::N1 * S); }
+  BABE_HD static void tables(unsigned short* T1, int tid) {
+    for (int m = tid; m < PL::N1; m += THREADS) T1[m] = (unsigned short)PL::t1(m);
+  }
+  // z[Nc] (natural order) -> tile, element n = r + N2 j at digit index T1[n mod N1]
+  BABE_HD static void load_natural(const float2* z, float2* A, const unsigned short* T1, int tile, int tid) {
+    const int col = tid % S, slot = tid / S, r = tile * S + col;
+    const bool live = r < PL::N2;
+    constexpr int STEP = (PL::N2 * SLOTS) % PL::N1;
+    int m = (r + PL::N2 * slot) % PL::N1;
+#pragma unroll 5
+    for (int j = slot; j < PL::N1; j += SLOTS) {
+      A[T1[m] * S + col] = live ? z[r + PL::N2 * j] : make_float2(0.f, 0.f);
+      m += STEP;
+      if (m >= PL::N1) m -= PL::N1;
+    }
+  }
+  BABE_HD static void store_natural(const float2* A, float2* z, const unsigned short* T1, int tile, int tid) {
+    const int col = tid % S, slot = tid / S, r = tile * S + col;
+    if (r >= PL::N2) return;
+    constexpr int STEP = (PL::N2 * SLOTS) % PL::N1;
+    int m = (r + PL::N2 * slot) % PL::N1;
+#pragma unroll 5
+    for (int j = slot; j < PL::N1; j += SLOTS) {
+      z[r + PL::N2 * j] = A[T1[m] * S + col];
+      m += STEP;
+      if (m >= PL::N1) m -= PL::N1;
+    }
+  }
+  // intermediate Y[q][r] (row pitch P2) <-> tile, digit index q in place
+  BABE_HD static void store_rows(const float2* A, float2* Y, int tile, int tid) {
+    const int col = tid % S, slot = tid / S, r = tile * S + col;
+    if (r >= PL::N2) return;
+#pragma unroll 5
+    for (int q = slot; q < PL::N1; q += SLOTS) Y[(size_t)q * PL::P2 + r] = A[q * S + col];
+  }
+  BABE_HD static void load_rows(const float2* Y, float2* A, int tile, int tid) {
+    const int col = tid % S, slot = tid / S, r = tile * S + col;
+    const bool live = r < PL::N2;
+#pragma unroll 5
+    for (int q = slot; q < PL::N1; q += SLOTS) A[q * S + col] = live ? Y[(size_t)q * PL::P2 + r] : make_float2(0.f, 0.f);
+  }
+  template <bool INV>
+  BABE_HD static void stage_a(float2* A, int tid) { stage<PL::RA, 1, PL::RB * PL::RC, S, INV>(A, tid / S, tid % S, SLOTS); }
+  template <bool INV>
+  BABE_HD static void stage_b(float2* A, int tid) { stage<PL::RB, PL::RA, PL::RC, S, INV>(A, tid / S, tid % S, SLOTS); }
+  template <bool INV>
+  BABE_HD static void stage_c(float2* A, int tid) { stage<PL::RC, PL::RA * PL::RB, 1, S, INV>(A, tid / S, tid % S, SLOTS); }
+  template <bool INV>
+  BABE_HD static void stages(float2* A, int tid) {     // device: all threads of the CTA; ends with a barrier
+    stage_a<INV>(A, tid); PFA_SYNC();
+    if (PL::RB > 1) { stage_b<INV>(A, tid); PFA_SYNC(); }
+    if (PL::RC > 1) { stage_c<INV>(A, tid); PFA_SYNC(); }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 2: digits of N2 for the rows of S/2 residue pairs (k1, N1 - k1); last tile: the self-mirrored k1 = 0, N1 / 2
+// ---------------------------------------------------------------------------------------------------------------------
+struct GatherTab {                 // synthesis: overlap-add of the band spectra, <= 4 bands per bin
+  const float2* BS;                // this row's band spectra [sum_lg]
+  const int4* src;                 // [Nc + 1] offsets into BS, -1: none
+};
+
+template <class PL, int S>
+struct Pass2 {
+  static constexpr int H = S / 2, SLOTS = THREADS / S, NP = (PL::N1 - 1) / 2, NTP = (NP + H - 1) / H, TILES = NTP + 1;
+  static constexpr int NT = (PL::N2 + 7) & ~7;
+  static constexpr size_t SMEM = sizeof(float2) * PL::N2 * S + 2 * sizeof(unsigned short) * NT;
+  BABE_HD static unsigned short* tab_t2(float2* A) { return reinterpret_cast<unsigned short*>(A + PL::N2 * S); }
+  BABE_HD static unsigned short* tab_d2(float2* A) { return tab_t2(A) + NT; }
+  BABE_HD static void tables(unsigned short* T2, unsigned short* D2, int tid) {
+    for (int r = tid; r < PL::N2; r += THREADS) { T2[r] = (unsigned short)PL::t2(r); D2[r] = (unsigned short)PL::d2(r); }
+  }
+  BABE_HD static int col_k1(int tile, int col) {               // -1: empty column
+    if (tile < NTP) {
+      const int lo = 1 + H * tile + (col % H);
+      if (lo > NP) return -1;
+      return col < H ? lo : PL::N1 - lo;
+    }
+    if (col == 0) return 0;
+    if (col == 1 && PL::N1 % 2 == 0) return PL::N1 / 2;
+    return -1;
+  }
+  // rows of the intermediate (contiguous in r): one lane per row, 16 bytes (two r) per access
+  BABE_HD static void load_rows(const float2* Y, float2* A, const unsigned short* T2, int tile, int tid) {
+    const int col = tid % S, slot = tid / S, k1 = col_k1(tile, col);
+    if (k1 < 0) return;
+    const float4* row = reinterpret_cast<const float4*>(Y + (size_t)PL::q1(k1) * PL::P2);
+#pragma unroll 5
+    for (int ch = slot; ch < PL::P2 / 2; ch += SLOTS) {
+      const float4 v = row[ch];
+      const int r = 2 * ch;
+      A[T2[r] * S + col] = make_float2(v.x, v.y);
+      if (r + 1 < PL::N2) A[T2[r + 1] * S + col] = make_float2(v.z, v.w);
+    }
+  }
+  BABE_HD static void store_rows(const float2* A, float2* Y, const unsigned short* T2, int tile, int tid) {
+    const int col = tid % S, slot = tid / S, k1 = col_k1(tile, col);
+    if (k1 < 0) return;
+    float4* row = reinterpret_cast<float4*>(Y + (size_t)PL::q1(k1) * PL::P2);
+#pragma unroll 5
+    for (int ch = slot; ch < PL::P2 / 2; ch += SLOTS) {
+      const int r = 2 * ch;
+      const float2 a = A[T2[r] * S + col];
+      const float2 b = r + 1 < PL::N2 ? A[T2[r + 1] * S + col] : make_float2(0.f, 0.f);
+      row[ch] = make_float4(a.x, a.y, b.x, b.y);
+    }
+  }
+  template <bool INV>
+  BABE_HD static void stage_d(float2* A, int tile, int tid) {
+    if (col_k1(tile, tid % S) >= 0) stage<PL::RD, 1, PL::RE * PL::RF, S, INV>(A, tid / S, tid % S, SLOTS);
+  }
+  template <bool INV>
+  BABE_HD static void stage_e(float2* A, int tile, int tid) {
+    if (col_k1(tile, tid % S) >= 0) stage<PL::RE, PL::RD, PL::RF, S, INV>(A, tid / S, tid % S, SLOTS);
+  }
+  template <bool INV>
+  BABE_HD static void stage_f(float2* A, int tile, int tid) {
+    if (col_k1(tile, tid % S) >= 0) stage<PL::RF, PL::RD * PL::RE, 1, S, INV>(A, tid / S, tid % S, SLOTS);
+  }
+  template <bool INV>
+  BABE_HD static void stages(float2* A, int tile, int tid) {
+    stage_d<INV>(A, tile, tid); PFA_SYNC();
+    if (PL::RE > 1) { stage_e<INV>(A, tile, tid); PFA_SYNC(); }
+    if (PL::RF > 1) { stage_f<INV>(A, tile, tid); PFA_SYNC(); }
+  }
+  // every bin pair (k, Nc - k), k <= Nc - k, whose members live in this tile: f(k, index of Z[k], index of Z[Nc - k])
+  template <class F>
+  BABE_HD static void for_pairs(const unsigned short* D2, int tile, int tid, F&& f) {
+    if (tile < NTP) {
+      for (int idx = tid; idx < H * PL::N2; idx += THREADS) {
+        const int i = idx % H, j = idx / H;
+        const int k1 = 1 + H * tile + i;
+        if (k1 > NP) continue;
+        const int k = k1 + PL::N1 * j, r2 = k % PL::N2;
+        f(k, D2[r2] * S + i, D2[r2 ? PL::N2 - r2 : 0] * S + i + H);
+      }
+    } else {
+      constexpr int NCOL = 1 + (PL::N1 % 2 == 0);
+      for (int idx = tid; idx < NCOL * PL::N2; idx += THREADS) {
+        const int c = idx % NCOL, j = idx / NCOL;
+        const int k = (c ? PL::N1 / 2 : 0) + PL::N1 * j;
+        if (2 * k > PL::NC) continue;
+        const int r2 = k % PL::N2;
+        f(k, D2[r2] * S + c, D2[r2 ? PL::N2 - r2 : 0] * S + c);
+      }
+    }
+  }
+  // r2c: Z (tile) -> X[Nc + 1] natural order, times the optional real bin scale
+  BABE_HD static void post_to_x(const float2* A, const unsigned short* D2, float2* X, const float2* twls,
+                                const float* scale, int tile, int tid) {
+    for_pairs(D2, tile, tid, [&](int k, int ia, int ib) {
+      const int kp = PL::NC - k;
+      float2 Xk, Xkp;
+      if (k == 0) {
+        const float2 z0 = A[ia];
+        Xk = make_float2(z0.x + z0.y, 0.f);
+        Xkp = make_float2(z0.x - z0.y, 0.f);
+      } else {
+        post_pair(A[ia], A[ib], tw_ls(twls, k), Xk, Xkp);
+      }
+      if (scale) { const float sk = scale[k], sp = scale[kp]; Xk.x *= sk; Xk.y *= sk; Xkp.x *= sp; Xkp.y *= sp; }
+      X[k] = Xk;
+      if (kp != k) X[kp] = Xkp;
+    });
+  }
+  // r2c, multiply by the real H, c2r -- in place (apply_hpf_DC)
+  BABE_HD static void mid_filter(float2* A, const unsigned short* D2, const float2* twls, const float* Hf, int tile,
+                                 int tid) {
+    for_pairs(D2, tile, tid, [&](int k, int ia, int ib) {
+      const int kp = PL::NC - k;
+      const float2 W = tw_ls(twls, k);
+      float2 Xk, Xkp;
+      if (k == 0) {
+        const float2 z0 = A[ia];
+        Xk = make_float2(z0.x + z0.y, 0.f);
+        Xkp = make_float2(z0.x - z0.y, 0.f);
+      } else {
+        post_pair(A[ia], A[ib], W, Xk, Xkp);
+      }
+      const float hk = Hf[k], hp = Hf[kp];
+      Xk.x *= hk; Xk.y *= hk; Xkp.x *= hp; Xkp.y *= hp;
+      float2 Zk, Zkp;
+      pre_pair(Xk, Xkp, W, 1.0f / (float)PL::NC, Zk, Zkp);          // conj(Z) / Nc
+      A[ia] = make_float2(Zk.x, -Zk.y);
+      if (k != 0 && kp != k) A[ib] = make_float2(Zkp.x, -Zkp.y);
+    });
+  }
+  BABE_HD static float2 gather(const GatherTab& g, int k) {
+    const int4 s = g.src[k];
+    float2 v = make_float2(0.f, 0.f);
+    if (s.x >= 0) { const float2 t = g.BS[s.x]; v.x += t.x; v.y += t.y; }
+    if (s.y >= 0) { const float2 t = g.BS[s.y]; v.x += t.x; v.y += t.y; }
+    if (s.z >= 0) { const float2 t = g.BS[s.z]; v.x += t.x; v.y += t.y; }
+    if (s.w >= 0) { const float2 t = g.BS[s.w]; v.x += t.x; v.y += t.y; }
+    return v;
+  }
+  // c2r: X[Nc + 1] (or the gathered band spectra), times the optional bin scale -> Z / Nc (tile)
+  template <bool GATHER>
+  BABE_HD static void pre_from_x(float2* A, const unsigned short* D2, const float2* X, const GatherTab& g,
+                                 const float2* twls, const float* scale, int tile, int tid) {
+    for_pairs(D2, tile, tid, [&](int k, int ia, int ib) {
+      const int kp = PL::NC - k;
+      float2 a = GATHER ? gather(g, k) : X[k], b = GATHER ? gather(g, kp) : X[kp];
+      if (scale) { const float sk = scale[k], sp = scale[kp]; a.x *= sk; a.y *= sk; b.x *= sp; b.y *= sp; }
+      if (k == 0) { a.y = 0.f; b.y = 0.f; }
+      float2 Zk, Zkp;
+      pre_pair(a, b, tw_ls(twls, k), 1.0f / (float)PL::NC, Zk, Zkp);
+      A[ia] = make_float2(Zk.x, -Zk.y);
+      if (k != 0 && kp != k) A[ib] = make_float2(Zkp.x, -Zkp.y);
+    });
+  }
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels: grid (tiles, rows)
+// ---------------------------------------------------------------------------------------------------------------------
+template <class PL, int S>
+__global__ void __launch_bounds__(THREADS, 4) k_pfa1_fwd(const float2* __restrict__ x, float2* __restrict__ Y) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using P = Pass1<PL, S>;
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  unsigned short* T1 = P::table(A);
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  P::tables(T1, tid);
+  __syncthreads();
+  P::load_natural(x + (size_t)blockIdx.y * PL::NC, A, T1, tile, tid);
+  __syncthreads();
+  P::template stages<false>(A, tid);
+  P::store_rows(A, Y + (size_t)blockIdx.y * PL::N1 * PL::P2, tile, tid);
+}
+
+template <class PL, int S>
+__global__ void __launch_bounds__(THREADS, 4) k_pfa1_inv(const float2* __restrict__ Y, float2* __restrict__ x) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using P = Pass1<PL, S>;
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  unsigned short* T1 = P::table(A);
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  P::tables(T1, tid);
+  P::load_rows(Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
+  __syncthreads();
+  P::template stages<true>(A, tid);
+  P::store_natural(A, x + (size_t)blockIdx.y * PL::NC, T1, tile, tid);
+}
+
+struct P2Args {
+  const float2* Y;         // intermediate in  [rows][N1][P2]
+  float2* Yout;            // intermediate out [rows][N1][P2]
+  const float2* X;         // half spectrum in  [rows][Nc + 1]
+  float2* Xout;            // half spectrum out [rows][Nc + 1]
+  const float2* BS;        // band spectra [rows][sum_lg]
+  const int4* src;         // gather table [Nc + 1]
+  int sum_lg;
+  const float2* tw_ls;
+  const float* scale;      // optional bin scale / the filter H
+};
+
+// forward pass 2 + r2c -> X
+template <class PL, int S>
+__global__ void __launch_bounds__(THREADS, 4) k_pfa2_fwd(const P2Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using P = Pass2<PL, S>;
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  unsigned short *T2 = P::tab_t2(A), *D2 = P::tab_d2(A);
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  P::tables(T2, D2, tid);
+  __syncthreads();
+  P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, T2, tile, tid);
+  __syncthreads();
+  P::template stages<false>(A, tile, tid);
+  P::post_to_x(A, D2, a.Xout + (size_t)blockIdx.y * (PL::NC + 1), a.tw_ls, a.scale, tile, tid);
+}
+
+// forward pass 2, r2c, * H, c2r, inverse pass 2 (apply_hpf_DC)
+template <class PL, int S>
+__global__ void __launch_bounds__(THREADS, 4) k_pfa2_mid(const P2Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using P = Pass2<PL, S>;
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  unsigned short *T2 = P::tab_t2(A), *D2 = P::tab_d2(A);
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  P::tables(T2, D2, tid);
+  __syncthreads();
+  P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, T2, tile, tid);
+  __syncthreads();
+  P::template stages<false>(A, tile, tid);
+  P::mid_filter(A, D2, a.tw_ls, a.scale, tile, tid);
+  __syncthreads();
+  P::template stages<true>(A, tile, tid);
+  P::store_rows(A, a.Yout + (size_t)blockIdx.y * PL::N1 * PL::P2, T2, tile, tid);
+}
+
+// c2r from X (or gathered from the band spectra) + inverse pass 2
+template <class PL, int S, bool GATHER>
+__global__ void __launch_bounds__(THREADS, 4) k_pfa2_inv(const P2Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using P = Pass2<PL, S>;
+  float2* A = reinterpret_cast<float2*>(smem_raw);
+  unsigned short *T2 = P::tab_t2(A), *D2 = P::tab_d2(A);
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  P::tables(T2, D2, tid);
+  __syncthreads();
+  GatherTab g{GATHER ? a.BS + (size_t)blockIdx.y * a.sum_lg : nullptr, a.src};
+  P::template pre_from_x<GATHER>(A, D2, GATHER ? nullptr : a.X + (size_t)blockIdx.y * (PL::NC + 1), g, a.tw_ls,
+                                 a.scale, tile, tid);
+  __syncthreads();
+  P::template stages<true>(A, tile, tid);
+  P::store_rows(A, a.Yout + (size_t)blockIdx.y * PL::N1 * PL::P2, T2, tile, tid);
+}
+#endif  // __CUDACC__
+
+}  // namespace pfa
+}  // namespace babe

@@ -127,15 +127,17 @@ def time_cqt():
     SRc, L = 22050, 184184
     cq = CQT_nsgt(7, 64, mode="oct", window=("kaiser", 1), fs=SRc, audio_len=L, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for B, variant in ((64, -1), (64, 0), (64, 1), (8, -1), (8, 0), (8, 1)):
+    for B, variant in ((64, 2), (64, -1), (8, 2), (8, -1)) + (((64, 0), (64, 1), (8, 0), (8, 1)) if 'tiled' in sys.argv else ()):
         lib().babe_set_cqt_variant(variant)
         xc = torch.randn(B, L, device=dev) * 0.063
         cs = cq.fwd(xc.unsqueeze(1))
+        Xs = cq.rfft(xc)
         cqb = B * (4 * L + 8 * cq.plan.coef_per_row)
         for name, fn, nb in (("cqt_analysis", lambda: cq.fwd(xc.unsqueeze(1)), cqb),
                              ("cqt_synthesis", lambda: cq.bwd(cs), cqb),
                              ("hpf_DC", lambda: cq.apply_hpf_DC(xc), B * 8 * L),
-                             ("rfft", lambda: cq.rfft(xc), B * 8 * L)):
+                             ("rfft", lambda: cq.rfft(xc), B * 8 * L),
+                             ("irfft", lambda: cq.irfft(Xs), B * 8 * L)):
             med, best = timeit(fn, flush=flush)
             print(json.dumps({"B": B, "cqt_variant": variant, "op": name, "ms": round(med, 4), "best_ms": round(best, 4),
                               "GBps": round(nb / med / 1e6, 1), "frac": round(nb / med / 1e6 / PEAK, 4)}))
@@ -165,6 +167,9 @@ def time_fit():
         print("  max rel diff new vs round-1:", rel(res[0], res[-1]))
     lib().babe_set_fused_variant(0)
 
+
+if __name__ == "__main__" and "cqt" in sys.argv[1:]:
+    lib().babe_set_cqt_variant(2)
 
 if __name__ == "__main__" and "fit" in sys.argv[1:]:
     time_fit()

@@ -137,12 +137,14 @@ def test_planar_layout_matches_interleaved(CQT):
         assert rel_l2(gp.cpu(), torch.view_as_real(gc.squeeze(1)).permute(0, 3, 1, 2).cpu()) < 1e-6
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [-1, 0, 1])
 @pytest.mark.parametrize("numocts,binsoct,fs,Ls,B", [(4, 12, 22050, 8192, 3), (7, 64, 22050, 184184, 2),
                                                      (7, 64, 22050, 132300, 1), (8, 96, 44100, 485100, 1)])
 def test_tiled_passes_vs_oracle(CQT, variant, numocts, binsoct, fs, Ls, B):
-    """The alternative length-Ls transform (csrc/cqt_fft.cuh: tiles of 16 / 8 sequences, r2c post-, c2r pre-processing
-    and the synthesis gather fused into the passes; `babe_set_cqt_variant`) against the same oracle."""
+    """The other implementations of the length-Ls transform kept in the library (`babe_set_cqt_variant`: -1 = round 1's
+    generic passes, which also serve every length the prime-factor passes are not instantiated for; 0 / 1 = round 2's
+    tiled passes of csrc/cqt_fft.cuh) against the same oracle.  The default (2 = prime-factor passes of
+    csrc/cqt_pfa.cuh for Ls = 184184 and 368368) is what every other test in this file runs."""
     from babe_b200._lib import lib
     cq, ref = _pair(CQT, numocts, binsoct, fs, Ls)
     g = torch.Generator().manual_seed(Ls + 1)
@@ -161,4 +163,4 @@ def test_tiled_passes_vs_oracle(CQT, variant, numocts, binsoct, fs, Ls, B):
         assert rel_l2(cq.bwd(c).cpu().squeeze(1), ref.bwd(cr)) < TOL
         assert rel_l2(cq.apply_hpf_DC(xc).cpu(), ref.apply_hpf_DC(x.double())) < TOL
     finally:
-        lib().babe_set_cqt_variant(-1)
+        lib().babe_set_cqt_variant(2)

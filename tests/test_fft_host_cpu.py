@@ -184,3 +184,38 @@ def test_core4k_passes_on_host(tmp_path):
     for k in ("fwd_regs", "fwd_smem", "roundtrip_regs", "roundtrip_smem"):
         assert float(vals[k]) < 5e-7, (k, vals[k])
     assert float(vals["perm"]) == 0.0
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+@pytest.mark.parametrize("plan", [0, 1, 2, 3])
+def test_prime_factor_passes_on_host(tmp_path, plan):
+    """csrc/cqt_pfa.cuh: the prime-factor (Good-Thomas) two-pass transform of the CQT -- index maps, in-place odd-prime
+    DFT stages, r2c / c2r pair processing, the fused filter pass and the table-driven gather -- emulated thread by
+    thread on the host (tests/host/pfa_host_check.cu) against numpy's rfft / irfft.  Plans: two small ones (even and
+    odd N1), Ls = 184184 (BASELINE configs[1]) and Ls = 368368."""
+    import numpy as np
+    exe = str(tmp_path / "pfa_host_check")
+    src = os.path.join(ROOT, "tests", "host", "pfa_host_check.cu")
+    cmd = [NVCC, "-O1", "-std=c++17", "-o", exe, src, "-I", os.path.join(ROOT, "babe_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include")]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+    d = str(tmp_path)
+    subprocess.run([exe, str(plan), d], check=True, capture_output=True, timeout=600)
+    ld = lambda n, dt: np.fromfile(os.path.join(d, n), dtype=dt)
+    x, H, sc = (ld(n, np.float32).astype(np.float64) for n in ("x.f32", "H.f32", "scale.f32"))
+    X, y, xr, xg = ld("X.c64", np.complex64), ld("y.f32", np.float32), ld("xr.f32", np.float32), ld("xg.f32", np.float32)
+    BS, src_tab = ld("BS.c64", np.complex64).astype(np.complex128), ld("src.i32", np.int32).reshape(-1, 4)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    Xr = np.fft.rfft(x)
+    assert rel(X, Xr * sc) < 5e-7
+    assert rel(y, np.fft.irfft(Xr * H, n=len(x))) < 5e-7
+    Xin = X.astype(np.complex128) * H
+    Xin[0], Xin[-1] = Xin[0].real, Xin[-1].real
+    assert rel(xr, np.fft.irfft(Xin, n=len(x))) < 5e-7
+    G = np.zeros(len(src_tab), np.complex128)
+    for q in range(4):
+        m = src_tab[:, q] >= 0
+        G[m] += BS[src_tab[m, q]]
+    G *= sc
+    G[0], G[-1] = G[0].real, G[-1].real
+    assert rel(xg, np.fft.irfft(G, n=len(x))) < 5e-7
