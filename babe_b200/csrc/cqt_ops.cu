@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "bandfft.cuh"
+#include "bandfft_v.cuh"
 #include "smemfft.cuh"
 #include "rfft_pairs.cuh"
 #include "cqt_fft.cuh"
@@ -192,7 +193,7 @@ struct BandArgs {
   const float2* rootsm[BABE_MAX_OCTAVES];
   float2* coef[BABE_MAX_OCTAVES];        // per-octave coefficient tensors [B, binsoct, M] complex
   int planar;                            // 1: float [B, 2, binsoct, M] (re plane, im plane) instead
-  int B, rows_per_cta;
+  int B, rows_per_cta, band_variant;
   const int* band_p; const int* band_lg; const int* band_off;
   const float* win; const float* scale;
   const float2* X;                       // analysis: half spectrum [B, Nc+1]
@@ -356,7 +357,135 @@ __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int til
   }
 }
 
-// --- other octave sizes (M < 256): mixed-radix Stockham in shared memory ---------------------
+// --- octaves with M = 32 ... 4096: packed register FFT (bandfft_v.cuh), 4096 / M bands per CTA (M >= 256) ----------
+// Same data flow as band_tile_fast (next row prefetched with cp.async, window samples in shared memory), but the
+// transform works on float2 register pairs with the two-wide instructions, runs forward or inverse directly (no
+// conjugations), takes the window (and 1 / M) multiply in its first butterflies, and synchronises per band.
+template <class C, bool SYNTH>
+__device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, unsigned char* smem_raw) {
+  constexpr int NB = BAND_THREADS / C::TPB, M = C::M, NTWP = (C::NTW + 1) & ~1;
+  float2* exs = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = exs + ((NB * C::EXP + 1) & ~1);
+  float2* stage = tw + NTWP;                           // [16][BAND_THREADS]: input slot n1 of thread tid
+  float* wst = reinterpret_cast<float*>(stage + 16 * BAND_THREADS);
+  const int tid = threadIdx.x, bl = tid / C::TPB, t = tid % C::TPB;
+  const float2* roots_m = a.rootsm[o];
+  for (int i = tid; i < C::NTW; i += BAND_THREADS) tw[i] = C::twiddle(roots_m, i);
+  typename C::Regs rg;
+  C::init_regs(rg, roots_m, t);
+  const int band = tile * NB + bl;
+  const bool active = band < a.binsoct;
+  int p = 0, lg = 0, off = 0;
+  if (active) {
+    const int j = o * a.binsoct + band;
+    p = a.band_p[j]; lg = a.band_lg[j]; off = a.band_off[j];
+  }
+  const int half = lg / 2;
+  float2* ex = exs + bl * C::EXP;
+  unsigned valid = 0;
+  if (!SYNTH) {
+    // window sample (times the optional bin scale and 1 / M) of the thread's 16 INPUT slots; 0 = outside the window
+    const float inv_m = 1.0f / (float)M;
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      int i = C::in_slot(n1, t) + half;
+      if (i >= M) i -= M;
+      float w = 0.f;
+      const int k = p - half + i;
+      if (active && i < lg && k >= 0 && k <= a.Nc) {
+        w = a.win[off + i] * inv_m;
+        if (a.scale) w *= a.scale[k];
+        valid |= 1u << n1;
+      }
+      wst[n1 * BAND_THREADS + tid] = w;
+      stage[n1 * BAND_THREADS + tid] = make_float2(0.f, 0.f);
+    }
+  } else {
+    // dual-window sample of the thread's 16 OUTPUT slots
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      int i = C::out_slot(r, t) + half;
+      if (i >= M) i -= M;
+      wst[r * BAND_THREADS + tid] = (active && i < lg) ? a.win[off + i] : 0.f;
+    }
+  }
+  const int row0 = blockIdx.y * a.rows_per_cta;
+  const int row_end = min(a.B, (int)(blockIdx.y + 1) * a.rows_per_cta);
+  auto prefetch = [&](int row) {
+    if (!SYNTH) {
+      const float2* X = a.X + (size_t)row * (a.Nc + 1) + (p - half);
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        int i = C::in_slot(n1, t) + half;
+        if (i >= M) i -= M;
+        if (valid & (1u << n1)) cp_async8(stage + n1 * BAND_THREADS + tid, X + i);
+      }
+    } else if (active) {
+      if (!a.planar) {
+        const float2* in = a.coef[o] + ((size_t)row * a.binsoct + band) * M;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) cp_async8(stage + n1 * BAND_THREADS + tid, in + C::in_slot(n1, t));
+      } else {
+        const float* ire = reinterpret_cast<const float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + band) * M;
+        const float* iim = ire + (size_t)a.binsoct * M;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+          float* d = reinterpret_cast<float*>(stage + n1 * BAND_THREADS + tid);
+          cp_async4f(d, ire + C::in_slot(n1, t));
+          cp_async4f(d + 1, iim + C::in_slot(n1, t));
+        }
+      }
+    }
+  };
+  if (row0 < row_end) prefetch(row0);
+  __syncthreads();                                  // twiddle table
+  for (int row = row0; row < row_end; ++row) {
+    float2 z[16];
+    float s[16];
+    cp_async_commit_wait();                         // this thread's own copies: no barrier needed to read them
+    if (SYNTH && !active) {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) z[n1] = make_float2(0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) z[n1] = stage[n1 * BAND_THREADS + tid];
+    }
+    if (!SYNTH) {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) s[n1] = wst[n1 * BAND_THREADS + tid];
+    }
+    if (row + 1 < row_end) prefetch(row + 1);       // the staged values are in registers: the slots are free
+    C::template fwd<!SYNTH>(z, s, ex, tw, rg, t, 1 + bl);
+    if (active) {
+      if (!SYNTH) {
+        if (!a.planar) {
+          float2* out = a.coef[o] + ((size_t)row * a.binsoct + band) * M;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) out[C::out_slot(r, t)] = z[r];
+        } else {   // the layout the denoiser consumes (networks/cqtdiff+.py:750-753) without the transposing copy
+          float* ore = reinterpret_cast<float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + band) * M;
+          float* oim = ore + (size_t)a.binsoct * M;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            ore[C::out_slot(r, t)] = z[r].x;
+            oim[C::out_slot(r, t)] = z[r].y;
+          }
+        }
+      } else {
+        float2* BS = a.BS + (size_t)row * a.sum_lg + off;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          int i = C::out_slot(r, t) + half;
+          if (i >= M) i -= M;
+          if (i < lg) BS[i] = c_scale(z[r], wst[r * BAND_THREADS + tid]);
+        }
+      }
+    }
+    band_sync<C::TPB>(1 + bl);                      // the band's exchange buffer is reused by its next row
+  }
+}
+
+// --- other octave sizes: mixed-radix Stockham in shared memory -------------------------------
 template <bool SYNTH>
 __device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int tile, unsigned char* smem_raw) {
   const int M = a.M[o], S = padded_len(M), TB = a.tb[o];
@@ -458,12 +587,26 @@ __device__ __forceinline__ void band_tile(const BandArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
   const int tile = blockIdx.x - a.tile0[o];
-  switch (a.M[o]) {
-    case 256: band_tile_fast<1, SYNTH>(a, o, tile, smem_raw); break;
-    case 512: band_tile_fast<2, SYNTH>(a, o, tile, smem_raw); break;
-    case 1024: band_tile_fast<4, SYNTH>(a, o, tile, smem_raw); break;
-    case 2048: band_tile_fast<8, SYNTH>(a, o, tile, smem_raw); break;
-    case 4096: band_tile_fast<16, SYNTH>(a, o, tile, smem_raw); break;
+  if (a.band_variant == 0) {         // round-2 cores (A/B: babe_set_cqt_band_variant)
+    switch (a.M[o]) {
+      case 256: band_tile_fast<1, SYNTH>(a, o, tile, smem_raw); break;
+      case 512: band_tile_fast<2, SYNTH>(a, o, tile, smem_raw); break;
+      case 1024: band_tile_fast<4, SYNTH>(a, o, tile, smem_raw); break;
+      case 2048: band_tile_fast<8, SYNTH>(a, o, tile, smem_raw); break;
+      case 4096: band_tile_fast<16, SYNTH>(a, o, tile, smem_raw); break;
+      default: band_tile_generic<SYNTH>(a, o, tile, smem_raw); break;
+    }
+    return;
+  }
+  switch (a.M[o]) {                  // analysis = inverse transform of the windowed slice, synthesis = forward
+    case 32: band_tile_v<BandCoreS<2, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
+    case 64: band_tile_v<BandCoreS<4, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
+    case 128: band_tile_v<BandCoreS<8, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
+    case 256: band_tile_v<BandCoreV<1, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
+    case 512: band_tile_v<BandCoreV<2, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
+    case 1024: band_tile_v<BandCoreV<4, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
+    case 2048: band_tile_v<BandCoreV<8, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
+    case 4096: band_tile_v<BandCoreV<16, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
     default: band_tile_generic<SYNTH>(a, o, tile, smem_raw); break;
   }
 }
@@ -802,6 +945,8 @@ static int tiled_irfft(const babe_cqt_plan* p, const float2* X, const float2* BS
   return launch_f1(p, tmp, x, B, 0, 1, st);
 }
 
+// 1 (default): packed band cores (bandfft_v.cuh); 0: round 2's BandCore / generic Stockham
+static int g_band_variant = 1;
 static inline int band_r3(int M) {     // M = 256 * R3 handled by BandCore<R3>, else 0
   switch (M) { case 256: return 1; case 512: return 2; case 1024: return 4; case 2048: return 8;
                case 4096: return 16; default: return 0; }
@@ -817,7 +962,12 @@ static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int
     const int r3 = band_r3(M);
     int tb;
     size_t need;
-    if (r3) {                                  // register FFT: 4096 points per CTA
+    if (g_band_variant != 0 && (M == 32 || M == 64 || M == 128)) {   // BandCoreS<R2>: R2 threads per band
+      const int r2 = M / 16;
+      tb = BAND_THREADS / r2;
+      need = sizeof(float2) * ((size_t)((tb * (16 * (r2 + 1) + r2) + 1) & ~1) + 2 + 16 * BAND_THREADS) +
+             sizeof(float) * 16 * BAND_THREADS;
+    } else if (r3) {                           // register FFT: 4096 points per CTA
       tb = 16 / r3;
       need = sizeof(float2) * ((size_t)tb * 16 * (16 * r3 + 1) + 16 * r3 + 16 * BAND_THREADS) +
              sizeof(float) * 16 * BAND_THREADS;   // ex + twiddles + prefetch stage + window samples
@@ -835,7 +985,7 @@ static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int
   // rows per CTA: keep >= ~4 CTAs per SM in flight, amortise the per-CTA twiddle loads beyond that
   int rpc = 1;
   while (rpc < 8 && (long long)items * ((B + 2 * rpc - 1) / (2 * rpc)) >= 4LL * 148) rpc *= 2;
-  a.B = B; a.rows_per_cta = rpc;
+  a.B = B; a.rows_per_cta = rpc; a.band_variant = g_band_variant;
   return BABE_OK;
 }
 
@@ -1012,3 +1162,8 @@ extern "C" int babe_set_cqt_variant(int v) {
   return BABE_OK;
 }
 extern "C" int babe_get_cqt_variant(void) { return babe::g_cqt_variant; }
+extern "C" int babe_set_cqt_band_variant(int v) {
+  if (v < 0 || v > 1) return BABE_EBADARG;
+  babe::g_band_variant = v;
+  return BABE_OK;
+}

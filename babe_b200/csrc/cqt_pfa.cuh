@@ -119,6 +119,30 @@ BABE_HD void stage(float2* A, int slot, int col, int nslots) {
 #define PFA_SYNC() ((void)0)
 #endif
 
+// global -> shared copies that need no registers and no waiting until the tile is complete (LDGSTS); plain copies on the
+// host.  All loads of a tile are in flight at once: the load phase of a CTA costs one memory latency.
+BABE_HD void copy8_async(float2* dst, const float2* src) {
+#ifdef __CUDA_ARCH__
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+#else
+  *dst = *src;
+#endif
+}
+BABE_HD void copy16_async(float2* dst, const float2* src) {
+#ifdef __CUDA_ARCH__
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+#else
+  dst[0] = src[0]; dst[1] = src[1];
+#endif
+}
+BABE_HD void copies_wait() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // pass 1: digits of N1 for a tile of S residues r = n mod N2
 // ---------------------------------------------------------------------------------------------------------------------
@@ -136,12 +160,14 @@ struct Pass1 {
     const bool live = r < PL::N2;
     constexpr int STEP = (PL::N2 * SLOTS) % PL::N1;
     int m = (r + PL::N2 * slot) % PL::N1;
-#pragma unroll 5
+#pragma unroll 4
     for (int j = slot; j < PL::N1; j += SLOTS) {
-      A[T1[m] * S + col] = live ? z[r + PL::N2 * j] : make_float2(0.f, 0.f);
+      float2* dst = A + T1[m] * S + col;
+      if (live) copy8_async(dst, z + r + PL::N2 * j); else *dst = make_float2(0.f, 0.f);
       m += STEP;
       if (m >= PL::N1) m -= PL::N1;
     }
+    copies_wait();
   }
   BABE_HD static void store_natural(const float2* A, float2* z, const unsigned short* T1, int tile, int tid) {
     const int col = tid % S, slot = tid / S, r = tile * S + col;
@@ -157,16 +183,25 @@ struct Pass1 {
   }
   // intermediate Y[q][r] (row pitch P2) <-> tile, digit index q in place
   BABE_HD static void store_rows(const float2* A, float2* Y, int tile, int tid) {
-    const int col = tid % S, slot = tid / S, r = tile * S + col;
-    if (r >= PL::N2) return;
+    constexpr int HS = S / 2, SL2 = THREADS / HS;
+    const int c2 = 2 * (tid % HS), slot = tid / HS, r = tile * S + c2;
+    if (r >= PL::N2) return;          // r + 1 == N2 writes the pad element of the row (never read as data)
 #pragma unroll 5
-    for (int q = slot; q < PL::N1; q += SLOTS) Y[(size_t)q * PL::P2 + r] = A[q * S + col];
+    for (int q = slot; q < PL::N1; q += SL2)
+      *reinterpret_cast<float4*>(Y + (size_t)q * PL::P2 + r) = *reinterpret_cast<const float4*>(A + q * S + c2);
   }
+  // 16 bytes (two residues) per copy: rows of the intermediate and of the tile are 16-byte aligned
   BABE_HD static void load_rows(const float2* Y, float2* A, int tile, int tid) {
-    const int col = tid % S, slot = tid / S, r = tile * S + col;
-    const bool live = r < PL::N2;
-#pragma unroll 5
-    for (int q = slot; q < PL::N1; q += SLOTS) A[q * S + col] = live ? Y[(size_t)q * PL::P2 + r] : make_float2(0.f, 0.f);
+    constexpr int HS = S / 2, SL2 = THREADS / HS;
+    const int c2 = 2 * (tid % HS), slot = tid / HS, r = tile * S + c2;
+    const bool live = r < PL::N2;     // r + 1 == N2: the pad element of the row lands in a dead column
+#pragma unroll 4
+    for (int q = slot; q < PL::N1; q += SL2) {
+      float2* dst = A + q * S + c2;
+      if (live) copy16_async(dst, Y + (size_t)q * PL::P2 + r);
+      else { dst[0] = make_float2(0.f, 0.f); dst[1] = make_float2(0.f, 0.f); }
+    }
+    copies_wait();
   }
   template <bool INV>
   BABE_HD static void stage_a(float2* A, int tid) { stage<PL::RA, 1, PL::RB * PL::RC, S, INV>(A, tid / S, tid % S, SLOTS); }
@@ -194,11 +229,19 @@ template <class PL, int S>
 struct Pass2 {
   static constexpr int H = S / 2, SLOTS = THREADS / S, NP = (PL::N1 - 1) / 2, NTP = (NP + H - 1) / H, TILES = NTP + 1;
   static constexpr int NT = (PL::N2 + 7) & ~7;
-  static constexpr size_t SMEM = sizeof(float2) * PL::N2 * S + 2 * sizeof(unsigned short) * NT;
-  BABE_HD static unsigned short* tab_t2(float2* A) { return reinterpret_cast<unsigned short*>(A + PL::N2 * S); }
+  static constexpr size_t SMEM = sizeof(float2) * (PL::N2 * S + NT) + 2 * sizeof(unsigned short) * NT;
+  // shared memory: tile A [N2][S], TJ[j] = W_Ls^{N1 j} (the bin twiddles of a column are W_Ls^{k1} TJ[j]), T2, D2
+  BABE_HD static float2* tab_tj(float2* A) { return A + PL::N2 * S; }
+  BABE_HD static unsigned short* tab_t2(float2* A) { return reinterpret_cast<unsigned short*>(A + PL::N2 * S + NT); }
   BABE_HD static unsigned short* tab_d2(float2* A) { return tab_t2(A) + NT; }
-  BABE_HD static void tables(unsigned short* T2, unsigned short* D2, int tid) {
-    for (int r = tid; r < PL::N2; r += THREADS) { T2[r] = (unsigned short)PL::t2(r); D2[r] = (unsigned short)PL::d2(r); }
+  BABE_HD static void tables(float2* A, const float2* twls, int tid) {
+    float2* TJ = tab_tj(A);
+    unsigned short *T2 = tab_t2(A), *D2 = tab_d2(A);
+    for (int r = tid; r < PL::N2; r += THREADS) {
+      T2[r] = (unsigned short)PL::t2(r);
+      D2[r] = (unsigned short)PL::d2(r);
+      TJ[r] = tw_ls(twls, PL::N1 * r);
+    }
   }
   BABE_HD static int col_k1(int tile, int col) {               // -1: empty column
     if (tile < NTP) {
@@ -211,19 +254,21 @@ struct Pass2 {
     return -1;
   }
   // rows of the intermediate (contiguous in r): one lane per row, 16 bytes (two r) per access
-  BABE_HD static void load_rows(const float2* Y, float2* A, const unsigned short* T2, int tile, int tid) {
+  BABE_HD static void load_rows(const float2* Y, float2* A, int tile, int tid) {
+    const unsigned short* T2 = tab_t2(A);
     const int col = tid % S, slot = tid / S, k1 = col_k1(tile, col);
     if (k1 < 0) return;
-    const float4* row = reinterpret_cast<const float4*>(Y + (size_t)PL::q1(k1) * PL::P2);
+    const float2* row = Y + (size_t)PL::q1(k1) * PL::P2;
 #pragma unroll 5
     for (int ch = slot; ch < PL::P2 / 2; ch += SLOTS) {
-      const float4 v = row[ch];
       const int r = 2 * ch;
-      A[T2[r] * S + col] = make_float2(v.x, v.y);
-      if (r + 1 < PL::N2) A[T2[r + 1] * S + col] = make_float2(v.z, v.w);
+      copy8_async(A + T2[r] * S + col, row + r);
+      if (r + 1 < PL::N2) copy8_async(A + T2[r + 1] * S + col, row + r + 1);
     }
+    copies_wait();
   }
-  BABE_HD static void store_rows(const float2* A, float2* Y, const unsigned short* T2, int tile, int tid) {
+  BABE_HD static void store_rows(const float2* A, float2* Y, int tile, int tid) {
+    const unsigned short* T2 = tab_t2(const_cast<float2*>(A));
     const int col = tid % S, slot = tid / S, k1 = col_k1(tile, col);
     if (k1 < 0) return;
     float4* row = reinterpret_cast<float4*>(Y + (size_t)PL::q1(k1) * PL::P2);
@@ -253,16 +298,26 @@ struct Pass2 {
     if (PL::RE > 1) { stage_e<INV>(A, tile, tid); PFA_SYNC(); }
     if (PL::RF > 1) { stage_f<INV>(A, tile, tid); PFA_SYNC(); }
   }
-  // every bin pair (k, Nc - k), k <= Nc - k, whose members live in this tile: f(k, index of Z[k], index of Z[Nc - k])
+  // every bin pair (k, Nc - k), k <= Nc - k, whose members live in this tile:
+  //   f(k, index of Z[k], index of Z[Nc - k], W_Ls^k)
+  // pair tiles: thread = (pair slot i = tid % H, j = tid / H + 32 it); bin k = k1 + N1 j, k mod N2 advanced incrementally
   template <class F>
-  BABE_HD static void for_pairs(const unsigned short* D2, int tile, int tid, F&& f) {
+  BABE_HD static void for_pairs(const float2* A, const float2* twls, int tile, int tid, F&& f) {
+    const float2* TJ = tab_tj(const_cast<float2*>(A));
+    const unsigned short* D2 = tab_d2(const_cast<float2*>(A));
     if (tile < NTP) {
-      for (int idx = tid; idx < H * PL::N2; idx += THREADS) {
-        const int i = idx % H, j = idx / H;
-        const int k1 = 1 + H * tile + i;
-        if (k1 > NP) continue;
-        const int k = k1 + PL::N1 * j, r2 = k % PL::N2;
-        f(k, D2[r2] * S + i, D2[r2 ? PL::N2 - r2 : 0] * S + i + H);
+      static_assert(THREADS % H == 0, "pair slot must be fixed per thread");
+      constexpr int JSTEP = THREADS / H, RSTEP = ((PL::N1 % PL::N2) * JSTEP) % PL::N2;
+      const int i = tid % H, k1 = 1 + H * tile + i;
+      if (k1 > NP) return;
+      const float2 W1 = tw_ls(twls, k1);
+      int j = tid / H;
+      int r2 = (k1 + (PL::N1 % PL::N2) * j) % PL::N2;
+#pragma unroll 2
+      for (; j < PL::N2; j += JSTEP) {
+        f(k1 + PL::N1 * j, D2[r2] * S + i, D2[r2 ? PL::N2 - r2 : 0] * S + i + H, cmul(W1, TJ[j]));
+        r2 += RSTEP;
+        if (r2 >= PL::N2) r2 -= PL::N2;
       }
     } else {
       constexpr int NCOL = 1 + (PL::N1 % 2 == 0);
@@ -271,14 +326,14 @@ struct Pass2 {
         const int k = (c ? PL::N1 / 2 : 0) + PL::N1 * j;
         if (2 * k > PL::NC) continue;
         const int r2 = k % PL::N2;
-        f(k, D2[r2] * S + c, D2[r2 ? PL::N2 - r2 : 0] * S + c);
+        f(k, D2[r2] * S + c, D2[r2 ? PL::N2 - r2 : 0] * S + c, tw_ls(twls, k));
       }
     }
   }
   // r2c: Z (tile) -> X[Nc + 1] natural order, times the optional real bin scale
-  BABE_HD static void post_to_x(const float2* A, const unsigned short* D2, float2* X, const float2* twls,
-                                const float* scale, int tile, int tid) {
-    for_pairs(D2, tile, tid, [&](int k, int ia, int ib) {
+  BABE_HD static void post_to_x(const float2* A, float2* X, const float2* twls, const float* scale, int tile,
+                                int tid) {
+    for_pairs(A, twls, tile, tid, [&](int k, int ia, int ib, float2 W) {
       const int kp = PL::NC - k;
       float2 Xk, Xkp;
       if (k == 0) {
@@ -286,7 +341,7 @@ struct Pass2 {
         Xk = make_float2(z0.x + z0.y, 0.f);
         Xkp = make_float2(z0.x - z0.y, 0.f);
       } else {
-        post_pair(A[ia], A[ib], tw_ls(twls, k), Xk, Xkp);
+        post_pair(A[ia], A[ib], W, Xk, Xkp);
       }
       if (scale) { const float sk = scale[k], sp = scale[kp]; Xk.x *= sk; Xk.y *= sk; Xkp.x *= sp; Xkp.y *= sp; }
       X[k] = Xk;
@@ -294,11 +349,9 @@ struct Pass2 {
     });
   }
   // r2c, multiply by the real H, c2r -- in place (apply_hpf_DC)
-  BABE_HD static void mid_filter(float2* A, const unsigned short* D2, const float2* twls, const float* Hf, int tile,
-                                 int tid) {
-    for_pairs(D2, tile, tid, [&](int k, int ia, int ib) {
+  BABE_HD static void mid_filter(float2* A, const float2* twls, const float* Hf, int tile, int tid) {
+    for_pairs(A, twls, tile, tid, [&](int k, int ia, int ib, float2 W) {
       const int kp = PL::NC - k;
-      const float2 W = tw_ls(twls, k);
       float2 Xk, Xkp;
       if (k == 0) {
         const float2 z0 = A[ia];
@@ -326,15 +379,15 @@ struct Pass2 {
   }
   // c2r: X[Nc + 1] (or the gathered band spectra), times the optional bin scale -> Z / Nc (tile)
   template <bool GATHER>
-  BABE_HD static void pre_from_x(float2* A, const unsigned short* D2, const float2* X, const GatherTab& g,
-                                 const float2* twls, const float* scale, int tile, int tid) {
-    for_pairs(D2, tile, tid, [&](int k, int ia, int ib) {
+  BABE_HD static void pre_from_x(float2* A, const float2* X, const GatherTab& g, const float2* twls,
+                                 const float* scale, int tile, int tid) {
+    for_pairs(A, twls, tile, tid, [&](int k, int ia, int ib, float2 W) {
       const int kp = PL::NC - k;
       float2 a = GATHER ? gather(g, k) : X[k], b = GATHER ? gather(g, kp) : X[kp];
       if (scale) { const float sk = scale[k], sp = scale[kp]; a.x *= sk; a.y *= sk; b.x *= sp; b.y *= sp; }
       if (k == 0) { a.y = 0.f; b.y = 0.f; }
       float2 Zk, Zkp;
-      pre_pair(a, b, tw_ls(twls, k), 1.0f / (float)PL::NC, Zk, Zkp);
+      pre_pair(a, b, W, 1.0f / (float)PL::NC, Zk, Zkp);
       A[ia] = make_float2(Zk.x, -Zk.y);
       if (k != 0 && kp != k) A[ib] = make_float2(Zkp.x, -Zkp.y);
     });
@@ -392,14 +445,13 @@ __global__ void __launch_bounds__(THREADS, 4) k_pfa2_fwd(const P2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
-  unsigned short *T2 = P::tab_t2(A), *D2 = P::tab_d2(A);
   const int tid = threadIdx.x, tile = blockIdx.x;
-  P::tables(T2, D2, tid);
+  P::tables(A, a.tw_ls, tid);
   __syncthreads();
-  P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, T2, tile, tid);
+  P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
   __syncthreads();
   P::template stages<false>(A, tile, tid);
-  P::post_to_x(A, D2, a.Xout + (size_t)blockIdx.y * (PL::NC + 1), a.tw_ls, a.scale, tile, tid);
+  P::post_to_x(A, a.Xout + (size_t)blockIdx.y * (PL::NC + 1), a.tw_ls, a.scale, tile, tid);
 }
 
 // forward pass 2, r2c, * H, c2r, inverse pass 2 (apply_hpf_DC)
@@ -408,17 +460,16 @@ __global__ void __launch_bounds__(THREADS, 4) k_pfa2_mid(const P2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
-  unsigned short *T2 = P::tab_t2(A), *D2 = P::tab_d2(A);
   const int tid = threadIdx.x, tile = blockIdx.x;
-  P::tables(T2, D2, tid);
+  P::tables(A, a.tw_ls, tid);
   __syncthreads();
-  P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, T2, tile, tid);
+  P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
   __syncthreads();
   P::template stages<false>(A, tile, tid);
-  P::mid_filter(A, D2, a.tw_ls, a.scale, tile, tid);
+  P::mid_filter(A, a.tw_ls, a.scale, tile, tid);
   __syncthreads();
   P::template stages<true>(A, tile, tid);
-  P::store_rows(A, a.Yout + (size_t)blockIdx.y * PL::N1 * PL::P2, T2, tile, tid);
+  P::store_rows(A, a.Yout + (size_t)blockIdx.y * PL::N1 * PL::P2, tile, tid);
 }
 
 // c2r from X (or gathered from the band spectra) + inverse pass 2
@@ -427,16 +478,15 @@ __global__ void __launch_bounds__(THREADS, 4) k_pfa2_inv(const P2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
-  unsigned short *T2 = P::tab_t2(A), *D2 = P::tab_d2(A);
   const int tid = threadIdx.x, tile = blockIdx.x;
-  P::tables(T2, D2, tid);
+  P::tables(A, a.tw_ls, tid);
   __syncthreads();
   GatherTab g{GATHER ? a.BS + (size_t)blockIdx.y * a.sum_lg : nullptr, a.src};
-  P::template pre_from_x<GATHER>(A, D2, GATHER ? nullptr : a.X + (size_t)blockIdx.y * (PL::NC + 1), g, a.tw_ls,
-                                 a.scale, tile, tid);
+  P::template pre_from_x<GATHER>(A, GATHER ? nullptr : a.X + (size_t)blockIdx.y * (PL::NC + 1), g, a.tw_ls, a.scale,
+                                 tile, tid);
   __syncthreads();
   P::template stages<true>(A, tile, tid);
-  P::store_rows(A, a.Yout + (size_t)blockIdx.y * PL::N1 * PL::P2, T2, tile, tid);
+  P::store_rows(A, a.Yout + (size_t)blockIdx.y * PL::N1 * PL::P2, tile, tid);
 }
 #endif  // __CUDACC__
 

@@ -75,12 +75,16 @@ int babe_set_fused_variant(int variant);
 int babe_get_fused_variant(void);
 /* Which implementation computes the length-Ls real FFT / inverse of the CQT calls (babe_rfft, babe_irfft,
  * babe_spectral_filter, babe_cqt_analysis, babe_cqt_synthesis):
- *    0            tiled passes (csrc/cqt_fft.cuh): 16 sequences per CTA held [element][sequence], the r2c post-,
- *                 c2r pre-processing and the synthesis overlap-add gather fused into the passes (2 launches per
- *                 transform); measured 7-40 % slower on B200 (profiles/r02_cqt.md), kept for A/B;
- *   -1 (default)  the round-1 passes with separate post / pre / gather kernels. */
+ *    2 (default)  prime-factor passes (csrc/cqt_pfa.cuh) for the instantiated lengths (Ls = 184184, 368368):
+ *                 twiddle-free in-place stages, r2c / c2r / filter / synthesis gather fused into pass 2
+ *                 (2 launches per transform, 3 for the spectral filter); other lengths run variant -1;
+ *    0, 1         round 2's tiled passes (csrc/cqt_fft.cuh), 16 / 8 sequences per CTA -- slower, kept for A/B;
+ *   -1            the round-1 generic mixed-radix passes with separate post / pre / gather kernels. */
 int babe_set_cqt_variant(int variant);
 int babe_get_cqt_variant(void);
+/* Band kernels of babe_cqt_analysis / babe_cqt_synthesis: 1 (default) packed register FFTs with per-band
+ * synchronisation for every octave size 32 ... 4096 (csrc/bandfft_v.cuh); 0: round 2's cores (A/B). */
+int babe_set_cqt_band_variant(int variant);
 
 /* ---- a3/a12: fused STFT -> H -> iSTFT ---------------------------------- */
 /* Replaces apply_filter (utils/blind_bwe_utils.py:6-13) and

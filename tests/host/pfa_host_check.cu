@@ -80,34 +80,31 @@ static void run(const std::string& dir) {
   pass1_fwd(reinterpret_cast<const float2*>(x.data()), Y.data());
   for (int tile = 0; tile < P2::TILES; ++tile) {
     float2* A = reinterpret_cast<float2*>(smem2.data());
-    unsigned short *T2 = P2::tab_t2(A), *D2 = P2::tab_d2(A);
-    for (int t = 0; t < THREADS; ++t) P2::tables(T2, D2, t);
-    for (int t = 0; t < THREADS; ++t) P2::load_rows(Y.data(), A, T2, tile, t);
+    for (int t = 0; t < THREADS; ++t) P2::tables(A, twls.data(), t);
+    for (int t = 0; t < THREADS; ++t) P2::load_rows(Y.data(), A, tile, t);
     stages2(A, tile, false);
-    for (int t = 0; t < THREADS; ++t) P2::post_to_x(A, D2, X.data(), twls.data(), scale.data(), tile, t);
+    for (int t = 0; t < THREADS; ++t) P2::post_to_x(A, X.data(), twls.data(), scale.data(), tile, t);
   }
   // ---- spectral filter: y = irfft(rfft(x) H)
   for (int tile = 0; tile < P2::TILES; ++tile) {
     float2* A = reinterpret_cast<float2*>(smem2.data());
-    unsigned short *T2 = P2::tab_t2(A), *D2 = P2::tab_d2(A);
-    for (int t = 0; t < THREADS; ++t) P2::tables(T2, D2, t);
-    for (int t = 0; t < THREADS; ++t) P2::load_rows(Y.data(), A, T2, tile, t);
+    for (int t = 0; t < THREADS; ++t) P2::tables(A, twls.data(), t);
+    for (int t = 0; t < THREADS; ++t) P2::load_rows(Y.data(), A, tile, t);
     stages2(A, tile, false);
-    for (int t = 0; t < THREADS; ++t) P2::mid_filter(A, D2, twls.data(), Hf.data(), tile, t);
+    for (int t = 0; t < THREADS; ++t) P2::mid_filter(A, twls.data(), Hf.data(), tile, t);
     stages2(A, tile, true);
-    for (int t = 0; t < THREADS; ++t) P2::store_rows(A, Y2.data(), T2, tile, t);
+    for (int t = 0; t < THREADS; ++t) P2::store_rows(A, Y2.data(), tile, t);
   }
   pass1_inv(Y2.data(), y.data());
   // ---- irfft(X * scale2) with scale2 = H
   GatherTab none{nullptr, nullptr};
   for (int tile = 0; tile < P2::TILES; ++tile) {
     float2* A = reinterpret_cast<float2*>(smem2.data());
-    unsigned short *T2 = P2::tab_t2(A), *D2 = P2::tab_d2(A);
-    for (int t = 0; t < THREADS; ++t) P2::tables(T2, D2, t);
+    for (int t = 0; t < THREADS; ++t) P2::tables(A, twls.data(), t);
     for (int t = 0; t < THREADS; ++t)
-      P2::template pre_from_x<false>(A, D2, X.data(), none, twls.data(), Hf.data(), tile, t);
+      P2::template pre_from_x<false>(A, X.data(), none, twls.data(), Hf.data(), tile, t);
     stages2(A, tile, true);
-    for (int t = 0; t < THREADS; ++t) P2::store_rows(A, Y2.data(), T2, tile, t);
+    for (int t = 0; t < THREADS; ++t) P2::store_rows(A, Y2.data(), tile, t);
   }
   pass1_inv(Y2.data(), xr.data());
   // ---- gather: every bin is the sum of 0..4 entries of a pool
@@ -124,12 +121,11 @@ static void run(const std::string& dir) {
   GatherTab g{BS.data(), src.data()};
   for (int tile = 0; tile < P2::TILES; ++tile) {
     float2* A = reinterpret_cast<float2*>(smem2.data());
-    unsigned short *T2 = P2::tab_t2(A), *D2 = P2::tab_d2(A);
-    for (int t = 0; t < THREADS; ++t) P2::tables(T2, D2, t);
+    for (int t = 0; t < THREADS; ++t) P2::tables(A, twls.data(), t);
     for (int t = 0; t < THREADS; ++t)
-      P2::template pre_from_x<true>(A, D2, nullptr, g, twls.data(), scale.data(), tile, t);
+      P2::template pre_from_x<true>(A, nullptr, g, twls.data(), scale.data(), tile, t);
     stages2(A, tile, true);
-    for (int t = 0; t < THREADS; ++t) P2::store_rows(A, Y2.data(), T2, tile, t);
+    for (int t = 0; t < THREADS; ++t) P2::store_rows(A, Y2.data(), tile, t);
   }
   pass1_inv(Y2.data(), xg.data());
   dump(dir, "x.f32", x.data(), x.size() * 4);

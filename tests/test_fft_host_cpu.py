@@ -219,3 +219,19 @@ def test_prime_factor_passes_on_host(tmp_path, plan):
     G *= sc
     G[0], G[-1] = G[0].real, G[-1].real
     assert rel(xg, np.fft.irfft(G, n=len(x))) < 5e-7
+
+
+@pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+def test_packed_band_cores_on_host(tmp_path):
+    """BandCoreV<R3> / BandCoreS<R2> (csrc/bandfft_v.cuh): the packed forward / inverse band transforms of the CQT
+    kernels (M = 32 ... 4096, window multiply folded into the first butterflies) emulated thread by thread."""
+    exe = str(tmp_path / "bandfft_v_host_check")
+    src = os.path.join(ROOT, "tests", "host", "bandfft_v_host_check.cu")
+    cmd = [NVCC, "-O1", "-std=c++17", "-o", exe, src, "-I", os.path.join(ROOT, "babe_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include")]
+    subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=600).stdout
+    rows = [l.split() for l in out.strip().splitlines()]
+    assert sorted({int(r[1]) for r in rows}) == [32, 64, 128, 256, 512, 1024, 2048, 4096] and len(rows) == 16
+    for r in rows:
+        assert float(r[4]) < 5e-7, r
