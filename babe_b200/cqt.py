@@ -145,10 +145,11 @@ class _Geometry:
         k = np.arange(Nc + 1)
         self.jlo = np.searchsorted(end, k, side="right").astype(np.int32)       # first j with end_j > k
         self.jhi = (np.searchsorted(start, k, side="right") - 1).astype(np.int32)  # last j with start_j <= k
-        # per-bin sources of the synthesis overlap-add: offsets into one row of band spectra, <= 4 bands per bin
+        # per-bin sources of the synthesis overlap-add: offsets into one row of band spectra, <= 3 bands per bin
+        # (int4 entries, the fourth is unused)
         cover = int((self.jhi - self.jlo + 1).max())
         self.bin_src = None
-        if cover <= 4:
+        if cover <= 3:
             src = np.full((Nc + 1, 4), -1, dtype=np.int32)
             for s in range(cover):
                 j = self.jlo.astype(np.int64) + s

@@ -14,6 +14,7 @@
 // available, see DESIGN.md "CQT parity".  Reference call sites:
 // networks/cqtdiff+.py:620,743,841; testing/blind_bwe_sampler.py:156.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -224,7 +225,8 @@ __device__ __forceinline__ void cp_async_commit_wait() {
 }
 
 template <int R3, bool SYNTH>
-__device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int tile, unsigned char* smem_raw) {
+__device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int tile, int row0, int row_end,
+                                               unsigned char* smem_raw) {
   using C = BandCore<R3>;
   constexpr int NB = BAND_THREADS / C::TPB, M = C::M;
   float2* exs = reinterpret_cast<float2*>(smem_raw);
@@ -274,8 +276,6 @@ __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int til
       wst[r * BAND_THREADS + tid] = (active && i < lg) ? a.win[off + i] : 0.f;
     }
   }
-  const int row0 = blockIdx.y * a.rows_per_cta;
-  const int row_end = min(a.B, (int)(blockIdx.y + 1) * a.rows_per_cta);
   auto prefetch = [&](int row) {
     if (!SYNTH) {
       const float2* X = a.X + (size_t)row * (a.Nc + 1) + (p - half);
@@ -362,7 +362,8 @@ __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int til
 // transform works on float2 register pairs with the two-wide instructions, runs forward or inverse directly (no
 // conjugations), takes the window (and 1 / M) multiply in its first butterflies, and synchronises per band.
 template <class C, bool SYNTH>
-__device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, unsigned char* smem_raw) {
+__device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, int row0, int row_end,
+                                            unsigned char* smem_raw) {
   constexpr int NB = BAND_THREADS / C::TPB, M = C::M, NTWP = (C::NTW + 1) & ~1;
   float2* exs = reinterpret_cast<float2*>(smem_raw);
   float2* tw = exs + ((NB * C::EXP + 1) & ~1);
@@ -409,8 +410,6 @@ __device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, 
       wst[r * BAND_THREADS + tid] = (active && i < lg) ? a.win[off + i] : 0.f;
     }
   }
-  const int row0 = blockIdx.y * a.rows_per_cta;
-  const int row_end = min(a.B, (int)(blockIdx.y + 1) * a.rows_per_cta);
   auto prefetch = [&](int row) {
     if (!SYNTH) {
       const float2* X = a.X + (size_t)row * (a.Nc + 1) + (p - half);
@@ -487,7 +486,8 @@ __device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, 
 
 // --- other octave sizes: mixed-radix Stockham in shared memory -------------------------------
 template <bool SYNTH>
-__device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int tile, unsigned char* smem_raw) {
+__device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int tile, int row0, int row_end,
+                                                  unsigned char* smem_raw) {
   const int M = a.M[o], S = padded_len(M), TB = a.tb[o];
   const int mshift = 31 - __clz(M);              // octave sizes are powers of two
   const int b0 = tile * TB;
@@ -505,8 +505,7 @@ __device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int 
   }
   __syncthreads();
   const float inv_m = 1.0f / (float)M;
-  const int row_end = min(a.B, (int)(blockIdx.y + 1) * a.rows_per_cta);
-  for (int row = blockIdx.y * a.rows_per_cta; row < row_end; ++row) {
+  for (int row = row0; row < row_end; ++row) {
     if (!SYNTH) {
       const float2* X = a.X + (size_t)row * (a.Nc + 1);
 #pragma unroll 4
@@ -583,32 +582,38 @@ __device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int 
 }
 
 template <bool SYNTH>
-__device__ __forceinline__ void band_tile(const BandArgs& a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int o = find_octave(a, blockIdx.x);
-  const int tile = blockIdx.x - a.tile0[o];
+__device__ __forceinline__ void band_segment(const BandArgs& a, int o, int tile, int row0, int row_end,
+                                             unsigned char* smem_raw) {
   if (a.band_variant == 0) {         // round-2 cores (A/B: babe_set_cqt_band_variant)
     switch (a.M[o]) {
-      case 256: band_tile_fast<1, SYNTH>(a, o, tile, smem_raw); break;
-      case 512: band_tile_fast<2, SYNTH>(a, o, tile, smem_raw); break;
-      case 1024: band_tile_fast<4, SYNTH>(a, o, tile, smem_raw); break;
-      case 2048: band_tile_fast<8, SYNTH>(a, o, tile, smem_raw); break;
-      case 4096: band_tile_fast<16, SYNTH>(a, o, tile, smem_raw); break;
-      default: band_tile_generic<SYNTH>(a, o, tile, smem_raw); break;
+      case 256: band_tile_fast<1, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+      case 512: band_tile_fast<2, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+      case 1024: band_tile_fast<4, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+      case 2048: band_tile_fast<8, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+      case 4096: band_tile_fast<16, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+      default: band_tile_generic<SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
     }
     return;
   }
   switch (a.M[o]) {                  // analysis = inverse transform of the windowed slice, synthesis = forward
-    case 32: band_tile_v<BandCoreS<2, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
-    case 64: band_tile_v<BandCoreS<4, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
-    case 128: band_tile_v<BandCoreS<8, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
-    case 256: band_tile_v<BandCoreV<1, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
-    case 512: band_tile_v<BandCoreV<2, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
-    case 1024: band_tile_v<BandCoreV<4, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
-    case 2048: band_tile_v<BandCoreV<8, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
-    case 4096: band_tile_v<BandCoreV<16, !SYNTH>, SYNTH>(a, o, tile, smem_raw); break;
-    default: band_tile_generic<SYNTH>(a, o, tile, smem_raw); break;
+    case 32: band_tile_v<BandCoreS<2, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    case 64: band_tile_v<BandCoreS<4, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    case 128: band_tile_v<BandCoreS<8, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    case 256: band_tile_v<BandCoreV<1, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    case 512: band_tile_v<BandCoreV<2, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    case 1024: band_tile_v<BandCoreV<4, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    case 2048: band_tile_v<BandCoreV<8, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    case 4096: band_tile_v<BandCoreV<16, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    default: band_tile_generic<SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
   }
+}
+
+template <bool SYNTH>
+__device__ __forceinline__ void band_tile(const BandArgs& a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int o = find_octave(a, blockIdx.x);
+  const int row0 = blockIdx.y * a.rows_per_cta;
+  band_segment<SYNTH>(a, o, blockIdx.x - a.tile0[o], row0, min(a.B, row0 + a.rows_per_cta), smem_raw);
 }
 
 // analysis: window multiply + fold + per-band inverse FFT of the half spectrum X
@@ -982,9 +987,12 @@ static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int
     smem = std::max(smem, need);
   }
   a.tile0[p->numocts] = items;
-  // rows per CTA: keep >= ~4 CTAs per SM in flight, amortise the per-CTA twiddle loads beyond that
+  // rows per CTA: as many as still fill one wave of 2 CTAs per SM -- the per-CTA preamble (twiddles, window samples,
+  // band descriptors: ~490 instructions per thread against ~670 per row) is amortised, and there is no partial
+  // second wave (measured at B = 64: 1 / 4 / 16 rows per CTA -> 0.181 / 0.142 / 0.136 ms; B = 8: 1 / 2 / 4 ->
+  // 0.047 / 0.043 / 0.044 ms, profiles/r02_cqt.md)
   int rpc = 1;
-  while (rpc < 8 && (long long)items * ((B + 2 * rpc - 1) / (2 * rpc)) >= 4LL * 148) rpc *= 2;
+  while (rpc < 16 && (long long)items * ((B + 2 * rpc - 1) / (2 * rpc)) >= (long long)(1.7 * sm_count())) rpc *= 2;
   a.B = B; a.rows_per_cta = rpc; a.band_variant = g_band_variant;
   return BABE_OK;
 }

@@ -160,14 +160,23 @@ struct Pass1 {
     const bool live = r < PL::N2;
     constexpr int STEP = (PL::N2 * SLOTS) % PL::N1;
     int m = (r + PL::N2 * slot) % PL::N1;
-#pragma unroll 4
-    for (int j = slot; j < PL::N1; j += SLOTS) {
-      float2* dst = A + T1[m] * S + col;
-      if (live) copy8_async(dst, z + r + PL::N2 * j); else *dst = make_float2(0.f, 0.f);
-      m += STEP;
-      if (m >= PL::N1) m -= PL::N1;
+    constexpr int IT = (PL::N1 + SLOTS - 1) / SLOTS, BATCH = 10;
+#pragma unroll
+    for (int b0 = 0; b0 < IT; b0 += BATCH) {
+      float2 v[BATCH];
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const int j = slot + (b0 + b) * SLOTS;
+        v[b] = (live && b0 + b < IT && j < PL::N1) ? z[r + PL::N2 * j] : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const int j = slot + (b0 + b) * SLOTS;
+        if (b0 + b < IT && j < PL::N1) A[T1[m] * S + col] = v[b];
+        m += STEP;
+        if (m >= PL::N1) m -= PL::N1;
+      }
     }
-    copies_wait();
   }
   BABE_HD static void store_natural(const float2* A, float2* z, const unsigned short* T1, int tile, int tid) {
     const int col = tid % S, slot = tid / S, r = tile * S + col;
@@ -220,7 +229,7 @@ struct Pass1 {
 // ---------------------------------------------------------------------------------------------------------------------
 // pass 2: digits of N2 for the rows of S/2 residue pairs (k1, N1 - k1); last tile: the self-mirrored k1 = 0, N1 / 2
 // ---------------------------------------------------------------------------------------------------------------------
-struct GatherTab {                 // synthesis: overlap-add of the band spectra, <= 4 bands per bin
+struct GatherTab {                 // synthesis: overlap-add of the band spectra, <= 3 bands per bin
   const float2* BS;                // this row's band spectra [sum_lg]
   const int4* src;                 // [Nc + 1] offsets into BS, -1: none
 };
@@ -258,14 +267,24 @@ struct Pass2 {
     const unsigned short* T2 = tab_t2(A);
     const int col = tid % S, slot = tid / S, k1 = col_k1(tile, col);
     if (k1 < 0) return;
-    const float2* row = Y + (size_t)PL::q1(k1) * PL::P2;
-#pragma unroll 5
-    for (int ch = slot; ch < PL::P2 / 2; ch += SLOTS) {
-      const int r = 2 * ch;
-      copy8_async(A + T2[r] * S + col, row + r);
-      if (r + 1 < PL::N2) copy8_async(A + T2[r + 1] * S + col, row + r + 1);
+    // 16-byte loads through registers, all of them issued before the first store: LDGSTS from 16 different rows
+    // would write shared memory lane by lane as the sectors arrive (measured: twice the wavefronts)
+    const float4* row = reinterpret_cast<const float4*>(Y + (size_t)PL::q1(k1) * PL::P2);
+    constexpr int NCH = PL::P2 / 2, IT = (NCH + SLOTS - 1) / SLOTS;
+    float4 v[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int ch = slot + it * SLOTS;
+      if (ch < NCH) v[it] = row[ch];
     }
-    copies_wait();
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int ch = slot + it * SLOTS, r = 2 * ch;
+      if (ch < NCH) {
+        A[T2[r] * S + col] = make_float2(v[it].x, v[it].y);
+        if (r + 1 < PL::N2) A[T2[r + 1] * S + col] = make_float2(v[it].z, v[it].w);
+      }
+    }
   }
   BABE_HD static void store_rows(const float2* A, float2* Y, int tile, int tid) {
     const unsigned short* T2 = tab_t2(const_cast<float2*>(A));
@@ -368,28 +387,77 @@ struct Pass2 {
       if (k != 0 && kp != k) A[ib] = make_float2(Zkp.x, -Zkp.y);
     });
   }
-  BABE_HD static float2 gather(const GatherTab& g, int k) {
-    const int4 s = g.src[k];
-    float2 v = make_float2(0.f, 0.f);
-    if (s.x >= 0) { const float2 t = g.BS[s.x]; v.x += t.x; v.y += t.y; }
-    if (s.y >= 0) { const float2 t = g.BS[s.y]; v.x += t.x; v.y += t.y; }
-    if (s.z >= 0) { const float2 t = g.BS[s.z]; v.x += t.x; v.y += t.y; }
-    if (s.w >= 0) { const float2 t = g.BS[s.w]; v.x += t.x; v.y += t.y; }
+  // overlap-add of the <= 3 band samples of bin k (GatherTab::src[k].xyz; w unused).  The loads are unconditional (a
+  // missing source reads entry 0 and is masked), so nothing but the table entry stands between them and their issue.
+  struct Src3 { float2 t0, t1, t2; };
+  BABE_HD static Src3 gather_load(const GatherTab& g, int4 s) {
+    Src3 d;
+    d.t0 = g.BS[max(s.x, 0)]; d.t1 = g.BS[max(s.y, 0)]; d.t2 = g.BS[max(s.z, 0)];
+    return d;
+  }
+  BABE_HD static float2 gather_sum(const Src3& d, int4 s) {
+    const float m0 = s.x >= 0 ? 1.f : 0.f, m1 = s.y >= 0 ? 1.f : 0.f, m2 = s.z >= 0 ? 1.f : 0.f;
+    float2 v = make_float2(d.t0.x * m0, d.t0.y * m0);
+    v.x = fmaf(d.t1.x, m1, v.x); v.y = fmaf(d.t1.y, m1, v.y);
+    v.x = fmaf(d.t2.x, m2, v.x); v.y = fmaf(d.t2.y, m2, v.y);
     return v;
+  }
+  BABE_HD static void pre_store(float2* A, int k, int ia, int ib, float2 a, float2 b, float2 W, const float* scale) {
+    const int kp = PL::NC - k;
+    if (scale) { const float sk = scale[k], sp = scale[kp]; a.x *= sk; a.y *= sk; b.x *= sp; b.y *= sp; }
+    if (k == 0) { a.y = 0.f; b.y = 0.f; }
+    float2 Zk, Zkp;
+    pre_pair(a, b, W, 1.0f / (float)PL::NC, Zk, Zkp);
+    A[ia] = make_float2(Zk.x, -Zk.y);
+    if (k != 0 && kp != k) A[ib] = make_float2(Zkp.x, -Zkp.y);
+  }
+  // Gather variant of the c2r prologue for the pair tiles, software-pipelined: the table entries are fetched two
+  // iterations ahead and the band samples one iteration ahead, so the dependent chain table -> sample (two L2
+  // latencies per pair in the plain loop: long_scoreboard 7.4 of 13 stall cycles per issue) is off the critical path.
+  BABE_HD static void pre_gather_pairs(float2* A, const GatherTab& g, const float2* twls, const float* scale, int tile,
+                                       int tid) {
+    const float2* TJ = tab_tj(A);
+    const unsigned short* D2 = tab_d2(A);
+    constexpr int JSTEP = THREADS / H, RSTEP = ((PL::N1 % PL::N2) * JSTEP) % PL::N2;
+    const int i = tid % H, k1 = 1 + H * tile + i;
+    if (k1 > NP) return;
+    const float2 W1 = tw_ls(twls, k1);
+    int j = tid / H;
+    int r2 = (k1 + (PL::N1 % PL::N2) * j) % PL::N2;
+    const int4 none = make_int4(-1, -1, -1, -1);
+    auto table = [&](int jj, int4& sa, int4& sb) {
+      sa = none; sb = none;
+      if (jj < PL::N2) { const int k = k1 + PL::N1 * jj; sa = g.src[k]; sb = g.src[PL::NC - k]; }
+    };
+    int4 sa0, sb0, sa1, sb1;
+    table(j, sa0, sb0);
+    table(j + JSTEP, sa1, sb1);
+    Src3 da0 = gather_load(g, sa0), db0 = gather_load(g, sb0);
+    for (; j < PL::N2; j += JSTEP) {
+      int4 sa2, sb2;
+      table(j + 2 * JSTEP, sa2, sb2);
+      const Src3 da1 = gather_load(g, sa1), db1 = gather_load(g, sb1);
+      pre_store(A, k1 + PL::N1 * j, D2[r2] * S + i, D2[r2 ? PL::N2 - r2 : 0] * S + i + H, gather_sum(da0, sa0),
+                gather_sum(db0, sb0), cmul(W1, TJ[j]), scale);
+      sa0 = sa1; sb0 = sb1; sa1 = sa2; sb1 = sb2; da0 = da1; db0 = db1;
+      r2 += RSTEP;
+      if (r2 >= PL::N2) r2 -= PL::N2;
+    }
   }
   // c2r: X[Nc + 1] (or the gathered band spectra), times the optional bin scale -> Z / Nc (tile)
   template <bool GATHER>
   BABE_HD static void pre_from_x(float2* A, const float2* X, const GatherTab& g, const float2* twls,
                                  const float* scale, int tile, int tid) {
+    if (GATHER && tile < NTP) { pre_gather_pairs(A, g, twls, scale, tile, tid); return; }
     for_pairs(A, twls, tile, tid, [&](int k, int ia, int ib, float2 W) {
-      const int kp = PL::NC - k;
-      float2 a = GATHER ? gather(g, k) : X[k], b = GATHER ? gather(g, kp) : X[kp];
-      if (scale) { const float sk = scale[k], sp = scale[kp]; a.x *= sk; a.y *= sk; b.x *= sp; b.y *= sp; }
-      if (k == 0) { a.y = 0.f; b.y = 0.f; }
-      float2 Zk, Zkp;
-      pre_pair(a, b, W, 1.0f / (float)PL::NC, Zk, Zkp);
-      A[ia] = make_float2(Zk.x, -Zk.y);
-      if (k != 0 && kp != k) A[ib] = make_float2(Zkp.x, -Zkp.y);
+      float2 a, b;
+      if (GATHER) {
+        const int4 sa = g.src[k], sb = g.src[PL::NC - k];
+        a = gather_sum(gather_load(g, sa), sa); b = gather_sum(gather_load(g, sb), sb);
+      } else {
+        a = X[k]; b = X[PL::NC - k];
+      }
+      pre_store(A, k, ia, ib, a, b, W, scale);
     });
   }
 };

@@ -213,9 +213,10 @@ typedef struct {
   const int* bin_jlo;          /* device int[Nc+1]: first band covering bin k */
   const int* bin_jhi;          /* device int[Nc+1]: last band covering bin k (jhi<jlo: none) */
   const int* bin_src;          /* device int[4*(Nc+1)] (16-byte aligned) or NULL: offsets into one row of the band
-                                  spectra (band_off[j] + k - (band_p[j] - band_lg[j]/2)) of the <= 4 bands that cover
-                                  bin k, -1 = none.  Lets the synthesis overlap-add run as a gather inside the
-                                  inverse transform; NULL (or a bin covered by > 4 bands): separate gather kernel. */
+                                  spectra (band_off[j] + k - (band_p[j] - band_lg[j]/2)) of the <= 3 bands that cover
+                                  bin k in entries 0..2, -1 = none, entry 3 unused.  Lets the synthesis overlap-add
+                                  run as a gather inside the inverse transform; NULL (a bin covered by > 3 bands):
+                                  separate gather kernel. */
 } babe_cqt_plan;
 
 /* bytes of scratch the calls below need for a batch of B rows */

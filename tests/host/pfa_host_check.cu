@@ -107,14 +107,14 @@ static void run(const std::string& dir) {
     for (int t = 0; t < THREADS; ++t) P2::store_rows(A, Y2.data(), tile, t);
   }
   pass1_inv(Y2.data(), xr.data());
-  // ---- gather: every bin is the sum of 0..4 entries of a pool
+  // ---- gather: every bin is the sum of 0..3 entries of a pool
   const int pool = 3 * (Nc + 1);
   std::vector<float2> BS(pool);
   for (auto& v : BS) v = make_float2(rnd(), rnd());
   std::vector<int4> src(Nc + 1);
   for (int k = 0; k <= Nc; ++k) {
     int s[4];
-    const int cnt = (k * 7 + 3) % 5;
+    const int cnt = (k * 7 + 3) % 4;
     for (int q = 0; q < 4; ++q) s[q] = q < cnt ? (int)(((long long)k * 2654435761LL + q * 40503) % pool) : -1;
     src[k] = make_int4(s[0], s[1], s[2], s[3]);
   }
