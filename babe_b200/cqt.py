@@ -150,7 +150,7 @@ class _Geometry:
         cover = int((self.jhi - self.jlo + 1).max())
         self.bin_src = None
         if cover <= 3:
-            src = np.full((Nc + 1, 4), -1, dtype=np.int32)
+            src = np.full((Nc + 1, 4), self.sum_lg, dtype=np.int32)    # sum_lg: the row's zero entry (no band)
             for s in range(cover):
                 j = self.jlo.astype(np.int64) + s
                 ok = j <= self.jhi

@@ -186,7 +186,7 @@ __global__ void k_spectral_mid(const float2* Z, float2* Zc, int Nc, const float2
 // constant-Q bands
 // ---------------------------------------------------------------------------
 struct BandArgs {
-  int Nc, numocts, binsoct, sum_lg;
+  int Nc, numocts, binsoct, sum_lg;          // sum_lg: row pitch of BS (samples + 2)
   int M[BABE_MAX_OCTAVES];
   int tb[BABE_MAX_OCTAVES];              // bands per CTA in octave o
   int tile0[BABE_MAX_OCTAVES + 1];       // first work item of octave o
@@ -612,8 +612,11 @@ template <bool SYNTH>
 __device__ __forceinline__ void band_tile(const BandArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
-  const int row0 = blockIdx.y * a.rows_per_cta;
-  band_segment<SYNTH>(a, o, blockIdx.x - a.tile0[o], row0, min(a.B, row0 + a.rows_per_cta), smem_raw);
+  const int row0 = blockIdx.y * a.rows_per_cta, row_end = min(a.B, row0 + a.rows_per_cta);
+  if (SYNTH && blockIdx.x == 0 && threadIdx.x < 2)          // the "no band" entries of the rows (a.sum_lg = pitch)
+    for (int row = row0; row < row_end; ++row)
+      a.BS[(size_t)row * a.sum_lg + a.sum_lg - 2 + threadIdx.x] = make_float2(0.f, 0.f);
+  band_segment<SYNTH>(a, o, blockIdx.x - a.tile0[o], row0, row_end, smem_raw);
 }
 
 // analysis: window multiply + fold + per-band inverse FFT of the half spectrum X
@@ -721,11 +724,14 @@ struct Workspace {
   float2 *bufA, *bufB, *bufX, *bufS;
 };
 
+// row pitch of the synthesis band spectra: sum_lg samples + a zero entry (two, for alignment) that the gather table
+// of the prime-factor inverse points at for "no band" (bin_src = sum_lg), written by k_cqt_synth_bands
+static int bs_pitch(const babe_cqt_plan* p) { return std::max(p->sum_lg, 0) + 2; }
 // per-row elements of the two pass buffers: the prime-factor intermediate pads its rows to an even pitch
 static size_t pass_row(const babe_cqt_plan* p) { return ((size_t)p->Nc + p->f1.n + 8) & ~(size_t)7; }
 static size_t ws_bytes(const babe_cqt_plan* p, int B) {
   return sizeof(float2) * (size_t)B * (2 * pass_row(p) + (((size_t)p->Nc + 8) & ~(size_t)7) +
-                                       (size_t)std::max(p->sum_lg, 0)) + 256;
+                                       (size_t)bs_pitch(p)) + 256;
 }
 
 static int carve(const babe_cqt_plan* p, int B, void* ws, size_t bytes, Workspace& w) {
@@ -777,7 +783,6 @@ static bool tiled_ok(const babe_cqt_plan* p) {
 // ---- third-generation length-Ls transform: prime-factor passes (cqt_pfa.cuh) -----------------------------------
 using Pfa92092 = pfa::Plan<4, 7, 11, 13, 23, 1>;      // Ls = 184184: 22.05 kHz x 8.35 s (BASELINE configs[1])
 using Pfa184184 = pfa::Plan<8, 7, 11, 13, 23, 1>;     // Ls = 368368: 44.1 kHz x 8.35 s (conf/exp/maestro44k_8s.yaml)
-constexpr int PFA_S = 16;
 
 static int pfa_id(const babe_cqt_plan* p) {
   if (g_cqt_variant != 2) return 0;
@@ -786,7 +791,8 @@ static int pfa_id(const babe_cqt_plan* p) {
   return 0;
 }
 
-template <class PL>
+// PFA_S: residues / rows per tile (16: 128-byte runs; 8 for small batches: twice the CTAs, half the latency each)
+template <class PL, int PFA_S>
 struct PfaRun {
   using P1 = pfa::Pass1<PL, PFA_S>;
   using P2 = pfa::Pass2<PL, PFA_S>;
@@ -823,7 +829,7 @@ struct PfaRun {
     pfa::P2Args a = args(p, scale);
     a.X = X; a.Yout = tmp;
     if (BS != nullptr) {
-      a.BS = BS; a.src = reinterpret_cast<const int4*>(p->bin_src); a.sum_lg = p->sum_lg;
+      a.BS = BS; a.src = reinterpret_cast<const int4*>(p->bin_src); a.sum_lg = bs_pitch(p);
       cudaFuncSetAttribute(pfa::k_pfa2_inv<PL, PFA_S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
       pfa::k_pfa2_inv<PL, PFA_S, true><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
     } else {
@@ -849,21 +855,26 @@ struct PfaRun {
   }
 };
 
+// 8-column tiles while 16-column tiles would leave SMs without a second CTA (B < ~16 rows)
+#define BABE_PFA_DISPATCH(call)                                                                   \
+  do {                                                                                            \
+    const bool small = (long long)B * ((Pfa92092::N2 + 15) / 16) < 2LL * sm_count();              \
+    if (pfa_id(p) == 1) return small ? PfaRun<Pfa92092, 8>::call : PfaRun<Pfa92092, 16>::call;    \
+    return small ? PfaRun<Pfa184184, 8>::call : PfaRun<Pfa184184, 16>::call;                      \
+  } while (0)
 static int pfa_rfft(const babe_cqt_plan* p, const float2* x, float2* tmp, float2* X, const float* scale, int B,
                     cudaStream_t st) {
-  return pfa_id(p) == 1 ? PfaRun<Pfa92092>::rfft(p, x, tmp, X, scale, B, st)
-                        : PfaRun<Pfa184184>::rfft(p, x, tmp, X, scale, B, st);
+  BABE_PFA_DISPATCH(rfft(p, x, tmp, X, scale, B, st));
 }
 static int pfa_irfft(const babe_cqt_plan* p, const float2* X, const float2* BS, float2* tmp, float2* x,
                      const float* scale, int B, cudaStream_t st) {
-  return pfa_id(p) == 1 ? PfaRun<Pfa92092>::irfft(p, X, BS, tmp, x, scale, B, st)
-                        : PfaRun<Pfa184184>::irfft(p, X, BS, tmp, x, scale, B, st);
+  BABE_PFA_DISPATCH(irfft(p, X, BS, tmp, x, scale, B, st));
 }
 static int pfa_filter(const babe_cqt_plan* p, const float2* x, float2* tmpA, float2* tmpB, float2* y,
                       const float* H, int B, cudaStream_t st) {
-  return pfa_id(p) == 1 ? PfaRun<Pfa92092>::filter(p, x, tmpA, tmpB, y, H, B, st)
-                        : PfaRun<Pfa184184>::filter(p, x, tmpA, tmpB, y, H, B, st);
+  BABE_PFA_DISPATCH(filter(p, x, tmpA, tmpB, y, H, B, st));
 }
+#undef BABE_PFA_DISPATCH
 
 static int launch_f1(const babe_cqt_plan* p, const float2* in, float2* out, int B, int twiddle, int conj_out,
                      cudaStream_t st) {
@@ -921,7 +932,7 @@ static int launch_f2_inv(const babe_cqt_plan* p, const float2* X, const float2* 
   const size_t smem = tile_fft_smem(a.N2, s8 ? 8 : 16);
   const dim3 grid(f2_grid(a.N1, s8 ? 4 : 8), B);
   if (BS != nullptr) {
-    a.BS = BS; a.sum_lg = p->sum_lg;
+    a.BS = BS; a.sum_lg = bs_pitch(p);
     a.band_p = p->band_p; a.band_lg = p->band_lg; a.band_off = p->band_off; a.jlo = p->bin_jlo; a.jhi = p->bin_jhi;
   }
 #define BABE_LAUNCH_INV(G, S)                                                                          \
@@ -958,7 +969,7 @@ static inline int band_r3(int M) {     // M = 256 * R3 handled by BandCore<R3>, 
 }
 
 static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int& items, int B) {
-  a.Nc = p->Nc; a.numocts = p->numocts; a.binsoct = p->binsoct; a.sum_lg = p->sum_lg;
+  a.Nc = p->Nc; a.numocts = p->numocts; a.binsoct = p->binsoct; a.sum_lg = bs_pitch(p);
   a.band_p = p->band_p; a.band_lg = p->band_lg; a.band_off = p->band_off;
   smem = 0;
   items = 0;
@@ -1152,7 +1163,7 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
   if (tiled_ok(plan))       // overlap-add gather + c2r pre-processing in the prologue of the inverse's first pass
     return tiled_irfft(plan, nullptr, w.bufS, w.bufA, reinterpret_cast<float2*>(x), bin_scale, B, st);
   GatherArgs g{};
-  g.BS = w.bufS; g.Zc = w.bufA; g.Nc = plan->Nc; g.sum_lg = plan->sum_lg;
+  g.BS = w.bufS; g.Zc = w.bufA; g.Nc = plan->Nc; g.sum_lg = bs_pitch(plan);
   g.band_p = plan->band_p; g.band_lg = plan->band_lg; g.band_off = plan->band_off;
   g.jlo = plan->bin_jlo; g.jhi = plan->bin_jhi; g.scale = bin_scale;
   g.tw_ls = reinterpret_cast<const float2*>(plan->tw_ls);

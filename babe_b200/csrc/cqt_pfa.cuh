@@ -231,7 +231,7 @@ struct Pass1 {
 // ---------------------------------------------------------------------------------------------------------------------
 struct GatherTab {                 // synthesis: overlap-add of the band spectra, <= 3 bands per bin
   const float2* BS;                // this row's band spectra [sum_lg]
-  const int4* src;                 // [Nc + 1] offsets into BS, -1: none
+  const int4* src;                 // [Nc + 1] offsets into BS (x, y, z); no band: the offset of a zero element
 };
 
 template <class PL, int S>
@@ -387,20 +387,16 @@ struct Pass2 {
       if (k != 0 && kp != k) A[ib] = make_float2(Zkp.x, -Zkp.y);
     });
   }
-  // overlap-add of the <= 3 band samples of bin k (GatherTab::src[k].xyz; w unused).  The loads are unconditional (a
-  // missing source reads entry 0 and is masked), so nothing but the table entry stands between them and their issue.
+  // overlap-add of the <= 3 band samples of bin k (GatherTab::src[k].xyz; w unused).  "No band" entries point at a
+  // zero element of the row, so the three loads are unconditional and unmasked.
   struct Src3 { float2 t0, t1, t2; };
   BABE_HD static Src3 gather_load(const GatherTab& g, int4 s) {
     Src3 d;
-    d.t0 = g.BS[max(s.x, 0)]; d.t1 = g.BS[max(s.y, 0)]; d.t2 = g.BS[max(s.z, 0)];
+    d.t0 = g.BS[s.x]; d.t1 = g.BS[s.y]; d.t2 = g.BS[s.z];
     return d;
   }
-  BABE_HD static float2 gather_sum(const Src3& d, int4 s) {
-    const float m0 = s.x >= 0 ? 1.f : 0.f, m1 = s.y >= 0 ? 1.f : 0.f, m2 = s.z >= 0 ? 1.f : 0.f;
-    float2 v = make_float2(d.t0.x * m0, d.t0.y * m0);
-    v.x = fmaf(d.t1.x, m1, v.x); v.y = fmaf(d.t1.y, m1, v.y);
-    v.x = fmaf(d.t2.x, m2, v.x); v.y = fmaf(d.t2.y, m2, v.y);
-    return v;
+  BABE_HD static float2 gather_sum(const Src3& d, int4) {
+    return make_float2(d.t0.x + d.t1.x + d.t2.x, d.t0.y + d.t1.y + d.t2.y);
   }
   BABE_HD static void pre_store(float2* A, int k, int ia, int ib, float2 a, float2 b, float2 W, const float* scale) {
     const int kp = PL::NC - k;
@@ -424,10 +420,9 @@ struct Pass2 {
     const float2 W1 = tw_ls(twls, k1);
     int j = tid / H;
     int r2 = (k1 + (PL::N1 % PL::N2) * j) % PL::N2;
-    const int4 none = make_int4(-1, -1, -1, -1);
-    auto table = [&](int jj, int4& sa, int4& sb) {
-      sa = none; sb = none;
-      if (jj < PL::N2) { const int k = k1 + PL::N1 * jj; sa = g.src[k]; sb = g.src[PL::NC - k]; }
+    auto table = [&](int jj, int4& sa, int4& sb) {       // past the end: re-read the last pair's entries (unused)
+      const int k = k1 + PL::N1 * min(jj, PL::N2 - 1);
+      sa = g.src[k]; sb = g.src[PL::NC - k];
     };
     int4 sa0, sb0, sa1, sb1;
     table(j, sa0, sb0);

@@ -214,7 +214,8 @@ typedef struct {
   const int* bin_jhi;          /* device int[Nc+1]: last band covering bin k (jhi<jlo: none) */
   const int* bin_src;          /* device int[4*(Nc+1)] (16-byte aligned) or NULL: offsets into one row of the band
                                   spectra (band_off[j] + k - (band_p[j] - band_lg[j]/2)) of the <= 3 bands that cover
-                                  bin k in entries 0..2, -1 = none, entry 3 unused.  Lets the synthesis overlap-add
+                                  bin k in entries 0..2, sum_lg = none (a zero entry the
+                                  library keeps behind each row), entry 3 unused.  Lets the synthesis overlap-add
                                   run as a gather inside the inverse transform; NULL (a bin covered by > 3 bands):
                                   separate gather kernel. */
 } babe_cqt_plan;

@@ -1,7 +1,7 @@
 // Host emulation of the prime-factor passes of csrc/cqt_pfa.cuh: every per-thread phase of k_pfa1_fwd, k_pfa2_fwd,
 // k_pfa2_mid, k_pfa2_inv (plain and gather) and k_pfa1_inv is run for all threads of all CTAs of one row, barrier by
 // barrier.  Writes x, H, scale, the gather inputs and the four results as raw float32 files into argv[2];
-// tests/test_fft_host_cpu.py compares them with numpy.   usage: pfa_host_check <plan: 0 | 1 | 2> <dir>
+// tests/test_fft_host_cpu.py compares them with numpy.   usage: pfa_host_check <plan: 0..5> <dir>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -109,13 +109,14 @@ static void run(const std::string& dir) {
   pass1_inv(Y2.data(), xr.data());
   // ---- gather: every bin is the sum of 0..3 entries of a pool
   const int pool = 3 * (Nc + 1);
-  std::vector<float2> BS(pool);
+  std::vector<float2> BS(pool + 1);
   for (auto& v : BS) v = make_float2(rnd(), rnd());
+  BS[pool] = make_float2(0.f, 0.f);                     // the "no band" entry
   std::vector<int4> src(Nc + 1);
   for (int k = 0; k <= Nc; ++k) {
     int s[4];
     const int cnt = (k * 7 + 3) % 4;
-    for (int q = 0; q < 4; ++q) s[q] = q < cnt ? (int)(((long long)k * 2654435761LL + q * 40503) % pool) : -1;
+    for (int q = 0; q < 4; ++q) s[q] = q < cnt ? (int)(((long long)k * 2654435761LL + q * 40503) % pool) : pool;
     src[k] = make_int4(s[0], s[1], s[2], s[3]);
   }
   GatherTab g{BS.data(), src.data()};
@@ -148,6 +149,8 @@ int main(int argc, char** argv) {
   else if (plan == 1) run<Plan<3, 5, 1, 4, 7, 1>, 16>(dir);         // odd N1: no self-mirrored k1 = N1 / 2
   else if (plan == 2) run<Plan<4, 7, 11, 13, 23, 1>, 16>(dir);      // Ls = 184184 (BASELINE configs[1])
   else if (plan == 3) run<Plan<8, 7, 11, 13, 23, 1>, 16>(dir);      // Ls = 368368 (44.1 kHz, 8.35 s)
+  else if (plan == 4) run<Plan<4, 7, 11, 13, 23, 1>, 8>(dir);       // 8-column tiles (small batches)
+  else if (plan == 5) run<Plan<4, 3, 1, 5, 7, 1>, 8>(dir);
   else return 1;
   return 0;
 }
