@@ -25,6 +25,7 @@
 // against numpy.  Lengths whose factorisation is not instantiated keep the generic passes of cqt_ops.cu.
 #pragma once
 #include "rfft_pairs.cuh"
+#include "fft16v.cuh"
 
 namespace babe {
 namespace pfa {
@@ -57,43 +58,52 @@ struct Plan {
 // exp(-2 pi i m / Ls) from the plan's two-level table
 BABE_HD float2 tw_ls(const float2* tab, int m) { return cmul(tab[m & (TW_LO_ - 1)], tab[TW_LO_ + (m >> 10)]); }
 
-// In-place DFT of the R points p[0], p[st], ..., p[(R-1) st]; INV: conjugated roots (no scaling).
+// In-place DFT of the R points p[0], p[st], ..., p[(R-1) st]; INV: conjugated roots (no scaling).  All arithmetic on
+// float2 register pairs with the two-wide instructions (fft16v.cuh): the odd-prime DFTs are FFMA2 with the root as a
+// 32-bit immediate broadcast to both halves -- half the issue slots of the scalar form, no constant registers.
 template <int R, bool INV>
 BABE_HD void dft_inplace(float2* p, const int st) {
   if constexpr (R == 1) {
     return;
-  } else if constexpr (R == 2 || R == 4 || R == 8 || R == 16) {
-    float re[R], im[R];
+  } else if constexpr (R == 2) {
+    const float2 u = p[0], v = p[st];
+    p[0] = c_add(u, v); p[st] = c_sub(u, v);
+  } else if constexpr (R == 4) {
+    float2 v0 = p[0], v1 = p[st], v2 = p[2 * st], v3 = p[3 * st];
+    fft4v<INV>(v0, v1, v2, v3);
+    p[0] = v0; p[st] = v1; p[2 * st] = v2; p[3 * st] = v3;
+  } else if constexpr (R == 8 || R == 16) {
+    float2 v[R];
 #pragma unroll
-    for (int t = 0; t < R; ++t) { const float2 v = p[t * st]; re[t] = v.x; im[t] = v.y; }
-    if (INV) butterfly<R>(im, re, nullptr, 0); else butterfly<R>(re, im, nullptr, 0);
+    for (int t = 0; t < R; ++t) v[t] = p[t * st];
+    if constexpr (R == 8) fft8v<INV, false>(v); else fft16v<INV>(v);
 #pragma unroll
-    for (int t = 0; t < R; ++t) p[t * st] = make_float2(re[t], im[t]);
+    for (int t = 0; t < R; ++t) p[t * st] = v[t];
   } else {
     // odd prime: a_t = v_t + v_{R-t}, b_t = v_t - v_{R-t};  X_u = v_0 + sum a_t cos - i sum b_t sin, X_{R-u} with + i
     constexpr int H = (R - 1) / 2;
     const float2 x0 = p[0];
-    float ar[H], ai[H], br[H], bi[H];
-    float s0r = x0.x, s0i = x0.y;
+    float2 a[H], b[H];
+    float2 s0 = x0;
 #pragma unroll
     for (int t = 1; t <= H; ++t) {
       const float2 u = p[t * st], v = p[(R - t) * st];
-      ar[t - 1] = u.x + v.x; ai[t - 1] = u.y + v.y;
-      br[t - 1] = u.x - v.x; bi[t - 1] = u.y - v.y;
-      s0r += ar[t - 1]; s0i += ai[t - 1];
+      a[t - 1] = c_add(u, v);
+      b[t - 1] = c_sub(u, v);
+      s0 = c_add(s0, a[t - 1]);
     }
-    p[0] = make_float2(s0r, s0i);
+    p[0] = s0;
 #pragma unroll
     for (int u = 1; u <= H; ++u) {
-      float Ar = x0.x, Ai = x0.y, Br = 0.f, Bi = 0.f;
+      float2 A = c_fma(a[0], odd_cos<R>(u % R), x0);
+      float2 B = c_scale(b[0], odd_sin<R>(u % R));
 #pragma unroll
-      for (int t = 1; t <= H; ++t) {
+      for (int t = 2; t <= H; ++t) {
         const int m = (t * u) % R;
-        const float c = odd_cos<R>(m), sn = odd_sin<R>(m);
-        Ar = fmaf(ar[t - 1], c, Ar); Ai = fmaf(ai[t - 1], c, Ai);
-        Br = fmaf(br[t - 1], sn, Br); Bi = fmaf(bi[t - 1], sn, Bi);
+        A = c_fma(a[t - 1], odd_cos<R>(m), A);
+        B = c_fma(b[t - 1], odd_sin<R>(m), B);
       }
-      const float2 lo = make_float2(Ar + Bi, Ai - Br), hi = make_float2(Ar - Bi, Ai + Br);   // A - iB, A + iB
+      const float2 lo = c_add_mi(A, B), hi = c_sub_mi(A, B);      // A - iB, A + iB
       p[u * st] = INV ? hi : lo;
       p[(R - u) * st] = INV ? lo : hi;
     }
