@@ -581,10 +581,12 @@ __device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int 
   }
 }
 
-template <bool SYNTH>
+// V: packed per-band cores (bandfft_v.cuh, default) / round 2's cores (A/B: babe_set_cqt_band_variant(0)).  Separate
+// kernels: one body with both sets inlined is 32 K SASS instructions.
+template <bool SYNTH, bool V>
 __device__ __forceinline__ void band_segment(const BandArgs& a, int o, int tile, int row0, int row_end,
                                              unsigned char* smem_raw) {
-  if (a.band_variant == 0) {         // round-2 cores (A/B: babe_set_cqt_band_variant)
+  if (!V) {
     switch (a.M[o]) {
       case 256: band_tile_fast<1, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
       case 512: band_tile_fast<2, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
@@ -608,7 +610,7 @@ __device__ __forceinline__ void band_segment(const BandArgs& a, int o, int tile,
   }
 }
 
-template <bool SYNTH>
+template <bool SYNTH, bool V>
 __device__ __forceinline__ void band_tile(const BandArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
@@ -616,13 +618,16 @@ __device__ __forceinline__ void band_tile(const BandArgs& a) {
   if (SYNTH && blockIdx.x == 0 && threadIdx.x < 2)          // the "no band" entries of the rows (a.sum_lg = pitch)
     for (int row = row0; row < row_end; ++row)
       a.BS[(size_t)row * a.sum_lg + a.sum_lg - 2 + threadIdx.x] = make_float2(0.f, 0.f);
-  band_segment<SYNTH>(a, o, blockIdx.x - a.tile0[o], row0, row_end, smem_raw);
+  band_segment<SYNTH, V>(a, o, blockIdx.x - a.tile0[o], row0, row_end, smem_raw);
 }
 
 // analysis: window multiply + fold + per-band inverse FFT of the half spectrum X
-__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_analysis(const BandArgs a) { band_tile<false>(a); }
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_analysis(const BandArgs a) { band_tile<false, true>(a); }
 // synthesis, first half: per-band FFT of the coefficients, dual-window multiply -> band spectra BS
-__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_synth_bands(const BandArgs a) { band_tile<true>(a); }
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_synth_bands(const BandArgs a) { band_tile<true, true>(a); }
+// the same on round 2's cores
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_analysis_r2(const BandArgs a) { band_tile<false, false>(a); }
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_synth_bands_r2(const BandArgs a) { band_tile<true, false>(a); }
 
 // overlap-add of the band spectra as a gather, fused with the c2r pre-processing
 struct GatherArgs {
@@ -1129,8 +1134,14 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
     a.coef[o] = reinterpret_cast<float2*>(out_octaves_host[o]);
   }
   a.win = win; a.scale = bin_scale; a.X = w.bufX; a.planar = planar ? 1 : 0;
-  cudaFuncSetAttribute(k_cqt_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_cqt_analysis<<<dim3(items, (B + a.rows_per_cta - 1) / a.rows_per_cta), BAND_THREADS, smem, st>>>(a);
+  const dim3 grid(items, (B + a.rows_per_cta - 1) / a.rows_per_cta);
+  if (a.band_variant) {
+    cudaFuncSetAttribute(k_cqt_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cqt_analysis<<<grid, BAND_THREADS, smem, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(k_cqt_analysis_r2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cqt_analysis_r2<<<grid, BAND_THREADS, smem, st>>>(a);
+  }
   return check_launch("k_cqt_analysis");
 }
 
@@ -1154,8 +1165,14 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
     a.coef[o] = const_cast<float2*>(reinterpret_cast<const float2*>(in_octaves_host[o]));
   }
   a.win = win; a.scale = nullptr; a.BS = w.bufS; a.planar = planar ? 1 : 0;
-  cudaFuncSetAttribute(k_cqt_synth_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_cqt_synth_bands<<<dim3(items, (B + a.rows_per_cta - 1) / a.rows_per_cta), BAND_THREADS, smem, st>>>(a);
+  const dim3 grid(items, (B + a.rows_per_cta - 1) / a.rows_per_cta);
+  if (a.band_variant) {
+    cudaFuncSetAttribute(k_cqt_synth_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cqt_synth_bands<<<grid, BAND_THREADS, smem, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(k_cqt_synth_bands_r2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cqt_synth_bands_r2<<<grid, BAND_THREADS, smem, st>>>(a);
+  }
   rc = check_launch("k_cqt_synth_bands");
   if (rc) return rc;
   if (pfa_id(plan) && plan->bin_src != nullptr)   // table-driven overlap-add gather in the prologue of the inverse pass 2

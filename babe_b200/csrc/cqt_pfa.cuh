@@ -115,7 +115,9 @@ template <int R, int CO, int CI, int S, bool INV>
 BABE_HD void stage(float2* A, int slot, int col, int nslots) {
   if constexpr (R > 1) {
     constexpr int NB = CO * CI;
-#pragma unroll 1
+    // small butterflies are mostly shared-memory latency: several of them in flight per thread
+    constexpr int UNROLL = R <= 4 ? 5 : (R <= 8 ? 2 : 1);
+#pragma unroll UNROLL
     for (int idx = slot; idx < NB; idx += nslots) {
       const int o = idx / CI, in = idx - o * CI;
       dft_inplace<R, INV>(A + ((o * R) * CI + in) * S + col, CI * S);
