@@ -788,11 +788,15 @@ static bool tiled_ok(const babe_cqt_plan* p) {
 // ---- third-generation length-Ls transform: prime-factor passes (cqt_pfa.cuh) -----------------------------------
 using Pfa92092 = pfa::Plan<4, 7, 11, 13, 23, 1>;      // Ls = 184184: 22.05 kHz x 8.35 s (BASELINE configs[1])
 using Pfa184184 = pfa::Plan<8, 7, 11, 13, 23, 1>;     // Ls = 368368: 44.1 kHz x 8.35 s (conf/exp/maestro44k_8s.yaml)
+using Pfa66150 = pfa::Plan<27, 25, 1, 49, 2, 1>;      // Ls = 132300: 22.05 kHz x 6 s (BASELINE configs[0]); prime powers as digits
+using Pfa242550 = pfa::Plan<25, 9, 2, 49, 11, 1>;     // Ls = 485100: 44.1 kHz x 11 s (conf/exp/maestro44k_8s.yaml)
 
 static int pfa_id(const babe_cqt_plan* p) {
   if (g_cqt_variant != 2) return 0;
   if (p->Nc == Pfa92092::NC) return 1;
   if (p->Nc == Pfa184184::NC) return 2;
+  if (p->Nc == Pfa66150::NC) return 3;
+  if (p->Nc == Pfa242550::NC) return 4;
   return 0;
 }
 
@@ -861,11 +865,19 @@ struct PfaRun {
 };
 
 // 8-column tiles while 16-column tiles would leave SMs without a second CTA (B < ~16 rows)
+#define BABE_PFA_DISPATCH_PLAN(PL, call)                                                          \
+  do {                                                                                            \
+    const bool small = (long long)B * ((PL::N2 + 15) / 16) < 2LL * sm_count();                    \
+    return small ? PfaRun<PL, 8>::call : PfaRun<PL, 16>::call;                                    \
+  } while (0)
 #define BABE_PFA_DISPATCH(call)                                                                   \
   do {                                                                                            \
-    const bool small = (long long)B * ((Pfa92092::N2 + 15) / 16) < 2LL * sm_count();              \
-    if (pfa_id(p) == 1) return small ? PfaRun<Pfa92092, 8>::call : PfaRun<Pfa92092, 16>::call;    \
-    return small ? PfaRun<Pfa184184, 8>::call : PfaRun<Pfa184184, 16>::call;                      \
+    switch (pfa_id(p)) {                                                                          \
+      case 1: BABE_PFA_DISPATCH_PLAN(Pfa92092, call);                                             \
+      case 2: BABE_PFA_DISPATCH_PLAN(Pfa184184, call);                                            \
+      case 3: BABE_PFA_DISPATCH_PLAN(Pfa66150, call);                                             \
+      default: BABE_PFA_DISPATCH_PLAN(Pfa242550, call);                                           \
+    }                                                                                             \
   } while (0)
 static int pfa_rfft(const babe_cqt_plan* p, const float2* x, float2* tmp, float2* X, const float* scale, int B,
                     cudaStream_t st) {
@@ -880,6 +892,7 @@ static int pfa_filter(const babe_cqt_plan* p, const float2* x, float2* tmpA, flo
   BABE_PFA_DISPATCH(filter(p, x, tmpA, tmpB, y, H, B, st));
 }
 #undef BABE_PFA_DISPATCH
+#undef BABE_PFA_DISPATCH_PLAN
 
 static int launch_f1(const babe_cqt_plan* p, const float2* in, float2* out, int B, int twiddle, int conj_out,
                      cudaStream_t st) {

@@ -1,7 +1,8 @@
 // Third-generation length-Ls transform of the CQT: a PRIME-FACTOR (Good-Thomas) FFT in two passes.
 //
 // Ls = 184184 = 2 * (4 * 7 * 11) * (13 * 23): all factors of Nc = Ls / 2 are pairwise coprime, so the complex FFT of
-// Nc points is a five-dimensional DFT with NO twiddle factors between any two stages:
+// Nc points is a five-dimensional DFT with NO twiddle factors between any two stages (for 132300 = 2 * 2 * 27 * 25 * 49
+// and 485100 the prime powers 9, 25, 27, 49 are single digits, transformed by the same mirrored-input odd DFT):
 //
 //     n = sum_i n_i * (Nc / R_i)  (mod Nc)      input index  (Ruritanian map; n_i = ((n mod R_i) * inv_i) mod R_i)
 //     k = k_i  (mod R_i)                        output index (Chinese remainder map)
@@ -45,6 +46,12 @@ struct Plan {
   static constexpr int RA = RA_, RB = RB_, RC = RC_, RD = RD_, RE = RE_, RF = RF_;
   static constexpr int N1 = RA * RB * RC, N2 = RD * RE * RF, NC = N1 * N2;
   static constexpr int P2 = (N2 + 1) & ~1;          // row pitch of the intermediate in float2 (even: 16-byte rows)
+  // resident CTAs per SM the register budget is sized for: the odd DFTs keep R - 1 float2 in registers
+  static constexpr int minb(int a, int b, int c) {
+    const int m = a > b ? (a > c ? a : c) : (b > c ? b : c);
+    return m <= 23 ? 4 : (m <= 27 ? 3 : 2);
+  }
+  static constexpr int MINB1 = minb(RA, RB, RC), MINB2 = minb(RD, RE, RF);
   static constexpr int IA = modinv((NC / RA) % RA, RA), IB = modinv((NC / RB) % RB, RB), IC = modinv((NC / RC) % RC, RC);
   static constexpr int ID = modinv((NC / RD) % RD, RD), IE = modinv((NC / RE) % RE, RE), IF_ = modinv((NC / RF) % RF, RF);
   // input side: digit index of residue m = n mod N1 (pass 1) / r = n mod N2 (pass 2)
@@ -474,7 +481,7 @@ struct Pass2 {
 // kernels: grid (tiles, rows)
 // ---------------------------------------------------------------------------------------------------------------------
 template <class PL, int S>
-__global__ void __launch_bounds__(THREADS, 4) k_pfa1_fwd(const float2* __restrict__ x, float2* __restrict__ Y) {
+__global__ void __launch_bounds__(THREADS, PL::MINB1) k_pfa1_fwd(const float2* __restrict__ x, float2* __restrict__ Y) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using P = Pass1<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(THREADS, 4) k_pfa1_fwd(const float2* __restric
 }
 
 template <class PL, int S>
-__global__ void __launch_bounds__(THREADS, 4) k_pfa1_inv(const float2* __restrict__ Y, float2* __restrict__ x) {
+__global__ void __launch_bounds__(THREADS, PL::MINB1) k_pfa1_inv(const float2* __restrict__ Y, float2* __restrict__ x) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using P = Pass1<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
@@ -516,7 +523,7 @@ struct P2Args {
 
 // forward pass 2 + r2c -> X
 template <class PL, int S>
-__global__ void __launch_bounds__(THREADS, 4) k_pfa2_fwd(const P2Args a) {
+__global__ void __launch_bounds__(THREADS, PL::MINB2) k_pfa2_fwd(const P2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(THREADS, 4) k_pfa2_fwd(const P2Args a) {
 
 // forward pass 2, r2c, * H, c2r, inverse pass 2 (apply_hpf_DC)
 template <class PL, int S>
-__global__ void __launch_bounds__(THREADS, 4) k_pfa2_mid(const P2Args a) {
+__global__ void __launch_bounds__(THREADS, PL::MINB2) k_pfa2_mid(const P2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(THREADS, 4) k_pfa2_mid(const P2Args a) {
 
 // c2r from X (or gathered from the band spectra) + inverse pass 2
 template <class PL, int S, bool GATHER>
-__global__ void __launch_bounds__(THREADS, 4) k_pfa2_inv(const P2Args a) {
+__global__ void __launch_bounds__(THREADS, PL::MINB2) k_pfa2_inv(const P2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);

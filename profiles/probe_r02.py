@@ -173,3 +173,26 @@ if __name__ == "__main__" and "cqt" in sys.argv[1:]:
 
 if __name__ == "__main__" and "fit" in sys.argv[1:]:
     time_fit()
+
+
+def time_cqt_lengths():
+    """The other segment lengths of the BASELINE configs: prime-factor passes (variant 2) against round 1's generic passes (-1)."""
+    from cqt_nsgt_pytorch import CQT_nsgt
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for fs, L, no, bo, B in ((22050, 132300, 7, 64, 64), (44100, 485100, 8, 96, 16), (44100, 368368, 8, 96, 16), (22050, 132300, 7, 64, 1)):
+        cq = CQT_nsgt(no, bo, mode="oct", window=("kaiser", 1), fs=fs, audio_len=L, device=dev)
+        xc = torch.randn(B, L, device=dev) * 0.063
+        for variant in (2, -1):
+            lib().babe_set_cqt_variant(variant)
+            cs = cq.fwd(xc.unsqueeze(1))
+            cqb = B * (4 * L + 8 * cq.plan.coef_per_row)
+            for name, fn, nb in (("cqt_analysis", lambda: cq.fwd(xc.unsqueeze(1)), cqb), ("cqt_synthesis", lambda: cq.bwd(cs), cqb),
+                                 ("hpf_DC", lambda: cq.apply_hpf_DC(xc), B * 8 * L), ("rfft", lambda: cq.rfft(xc), B * 8 * L)):
+                med, best = timeit(fn, flush=flush)
+                print(json.dumps({"Ls": L, "B": B, "cqt_variant": variant, "op": name, "ms": round(med, 4),
+                                  "GBps": round(nb / med / 1e6, 1), "frac": round(nb / med / 1e6 / PEAK, 4)}))
+    lib().babe_set_cqt_variant(2)
+
+
+if __name__ == "__main__" and "cqtlen" in sys.argv[1:]:
+    time_cqt_lengths()

@@ -1,7 +1,7 @@
 // Host emulation of the prime-factor passes of csrc/cqt_pfa.cuh: every per-thread phase of k_pfa1_fwd, k_pfa2_fwd,
 // k_pfa2_mid, k_pfa2_inv (plain and gather) and k_pfa1_inv is run for all threads of all CTAs of one row, barrier by
 // barrier.  Writes x, H, scale, the gather inputs and the four results as raw float32 files into argv[2];
-// tests/test_fft_host_cpu.py compares them with numpy.   usage: pfa_host_check <plan: 0..5> <dir>
+// tests/test_fft_host_cpu.py compares them with numpy.   usage: pfa_host_check <plan: 0..7> <dir>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -151,6 +151,8 @@ int main(int argc, char** argv) {
   else if (plan == 3) run<Plan<8, 7, 11, 13, 23, 1>, 16>(dir);      // Ls = 368368 (44.1 kHz, 8.35 s)
   else if (plan == 4) run<Plan<4, 7, 11, 13, 23, 1>, 8>(dir);       // 8-column tiles (small batches)
   else if (plan == 5) run<Plan<4, 3, 1, 5, 7, 1>, 8>(dir);
+  else if (plan == 6) run<Plan<27, 25, 1, 49, 2, 1>, 16>(dir);      // Ls = 132300 (prime powers 27, 25, 49 as single digits)
+  else if (plan == 7) run<Plan<25, 9, 2, 49, 11, 1>, 8>(dir);       // Ls = 485100
   else return 1;
   return 0;
 }

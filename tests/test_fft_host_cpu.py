@@ -187,12 +187,13 @@ def test_core4k_passes_on_host(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
-@pytest.mark.parametrize("plan", [0, 1, 2, 3])
+@pytest.mark.parametrize("plan", [0, 1, 2, 3, 4, 6, 7])
 def test_prime_factor_passes_on_host(tmp_path, plan):
     """csrc/cqt_pfa.cuh: the prime-factor (Good-Thomas) two-pass transform of the CQT -- index maps, in-place odd-prime
     DFT stages, r2c / c2r pair processing, the fused filter pass and the table-driven gather -- emulated thread by
     thread on the host (tests/host/pfa_host_check.cu) against numpy's rfft / irfft.  Plans: two small ones (even and
-    odd N1), Ls = 184184 (BASELINE configs[1]) and Ls = 368368."""
+    odd N1), Ls = 184184 (BASELINE configs[1]) with 16- and 8-column tiles, Ls = 368368, and the two lengths whose prime
+    powers are single digits (Ls = 132300 = 2 * 2 * 27 * 25 * 49, Ls = 485100 = 2 * 2 * 9 * 25 * 49 * 11)."""
     import numpy as np
     exe = str(tmp_path / "pfa_host_check")
     src = os.path.join(ROOT, "tests", "host", "pfa_host_check.cu")
