@@ -68,33 +68,39 @@ BABE_HD float2 tw_ls(const float2* tab, int m) { return cmul(tab[m & (TW_LO_ - 1
 // In-place DFT of the R points p[0], p[st], ..., p[(R-1) st]; INV: conjugated roots (no scaling).  All arithmetic on
 // float2 register pairs with the two-wide instructions (fft16v.cuh): the odd-prime DFTs are FFMA2 with the root as a
 // 32-bit immediate broadcast to both halves -- half the issue slots of the scalar form, no constant registers.
+template <int R, bool INV> BABE_HD void dft_io(const float2* q, const int sq, float2* p, const int st);
+// Inputs q[0], q[sq], ... and outputs p[0], p[st], ... may be the same array (all inputs are read before the first store)
+// or different ones (a stage that reads or writes the global intermediate directly).
 template <int R, bool INV>
-BABE_HD void dft_inplace(float2* p, const int st) {
+BABE_HD void dft_inplace(float2* p, const int st) { dft_io<R, INV>(p, st, p, st); }
+
+template <int R, bool INV>
+BABE_HD void dft_io(const float2* q, const int sq, float2* p, const int st) {
   if constexpr (R == 1) {
     return;
   } else if constexpr (R == 2) {
-    const float2 u = p[0], v = p[st];
+    const float2 u = q[0], v = q[sq];
     p[0] = c_add(u, v); p[st] = c_sub(u, v);
   } else if constexpr (R == 4) {
-    float2 v0 = p[0], v1 = p[st], v2 = p[2 * st], v3 = p[3 * st];
+    float2 v0 = q[0], v1 = q[sq], v2 = q[2 * sq], v3 = q[3 * sq];
     fft4v<INV>(v0, v1, v2, v3);
     p[0] = v0; p[st] = v1; p[2 * st] = v2; p[3 * st] = v3;
   } else if constexpr (R == 8 || R == 16) {
     float2 v[R];
 #pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = p[t * st];
+    for (int t = 0; t < R; ++t) v[t] = q[t * sq];
     if constexpr (R == 8) fft8v<INV, false>(v); else fft16v<INV>(v);
 #pragma unroll
     for (int t = 0; t < R; ++t) p[t * st] = v[t];
   } else {
     // odd prime: a_t = v_t + v_{R-t}, b_t = v_t - v_{R-t};  X_u = v_0 + sum a_t cos - i sum b_t sin, X_{R-u} with + i
     constexpr int H = (R - 1) / 2;
-    const float2 x0 = p[0];
+    const float2 x0 = q[0];
     float2 a[H], b[H];
     float2 s0 = x0;
 #pragma unroll
     for (int t = 1; t <= H; ++t) {
-      const float2 u = p[t * st], v = p[(R - t) * st];
+      const float2 u = q[t * sq], v = q[(R - t) * sq];
       a[t - 1] = c_add(u, v);
       b[t - 1] = c_sub(u, v);
       s0 = c_add(s0, a[t - 1]);
@@ -231,17 +237,56 @@ struct Pass1 {
     }
     copies_wait();
   }
-  template <bool INV>
-  BABE_HD static void stage_a(float2* A, int tid) { stage<PL::RA, 1, PL::RB * PL::RC, S, INV>(A, tid / S, tid % S, SLOTS); }
-  template <bool INV>
-  BABE_HD static void stage_b(float2* A, int tid) { stage<PL::RB, PL::RA, PL::RC, S, INV>(A, tid / S, tid % S, SLOTS); }
-  template <bool INV>
-  BABE_HD static void stage_c(float2* A, int tid) { stage<PL::RC, PL::RA * PL::RB, 1, S, INV>(A, tid / S, tid % S, SLOTS); }
-  template <bool INV>
-  BABE_HD static void stages(float2* A, int tid) {     // device: all threads of the CTA; ends with a barrier
-    stage_a<INV>(A, tid); PFA_SYNC();
-    if (PL::RB > 1) { stage_b<INV>(A, tid); PFA_SYNC(); }
-    if (PL::RC > 1) { stage_c<INV>(A, tid); PFA_SYNC(); }
+  // The stages in order (digits A, B, C; radix-1 digits skipped).  MODE 0: in place; MODE 1: inputs straight from the
+  // rows of the global intermediate (first stage of the inverse: no separate load pass); MODE 2: outputs straight to
+  // the rows of the global intermediate (last stage of the forward: no separate store pass).  Saves two of the eight
+  // shared-memory accesses per element and one barrier per tile.
+  static constexpr int NST = 1 + (PL::RB > 1) + (PL::RC > 1);
+  template <bool INV, int WHICH, int MODE>
+  BABE_HD static void run_stage(float2* A, const float2* Yin, float2* Yout, int tile, int tid) {
+    constexpr int R = WHICH == 0 ? PL::RA : (WHICH == 1 ? PL::RB : PL::RC);
+    constexpr int CO = WHICH == 0 ? 1 : (WHICH == 1 ? PL::RA : PL::RA * PL::RB);
+    constexpr int CI = WHICH == 0 ? PL::RB * PL::RC : (WHICH == 1 ? PL::RC : 1);
+    constexpr int NB = CO * CI, UNROLL = R <= 4 ? 5 : (R <= 8 ? 2 : 1);
+    const int col = tid % S, slot = tid / S, r = tile * S + col;
+    const bool live = r < PL::N2;
+#pragma unroll UNROLL
+    for (int idx = slot; idx < NB; idx += SLOTS) {
+      const int o = idx / CI, in = idx - o * CI, e0 = (o * R) * CI + in;
+      float2* a = A + e0 * S + col;
+      if (MODE == 0) {
+        dft_io<R, INV>(a, CI * S, a, CI * S);
+      } else if (MODE == 1) {
+        if (live) dft_io<R, INV>(Yin + (size_t)e0 * PL::P2 + r, CI * PL::P2, a, CI * S);
+        else {
+#pragma unroll
+          for (int d = 0; d < R; ++d) a[d * CI * S] = make_float2(0.f, 0.f);
+        }
+      } else {
+        if (live) dft_io<R, INV>(a, CI * S, Yout + (size_t)e0 * PL::P2 + r, CI * PL::P2);
+      }
+    }
+  }
+  // n-th executed stage (0 .. NST - 1) -> digit
+  static constexpr int which(int n) { return n == 0 ? 0 : (n == 1 ? (PL::RB > 1 ? 1 : 2) : 2); }
+  template <bool INV, int N, int MODE>
+  BABE_HD static void stage_n(float2* A, const float2* Yin, float2* Yout, int tile, int tid) {
+    if constexpr (N < NST) run_stage<INV, which(N), MODE>(A, Yin, Yout, tile, tid);
+  }
+  // forward: tile (filled by load_natural) -> rows of Y;  device: every thread of the CTA
+  BABE_HD static void forward_to_rows(float2* A, float2* Y, int tile, int tid) {
+    stage_n<false, 0, NST == 1 ? 2 : 0>(A, nullptr, Y, tile, tid);
+    if (NST > 1) { PFA_SYNC(); stage_n<false, 1, NST == 2 ? 2 : 0>(A, nullptr, Y, tile, tid); }
+    if (NST > 2) { PFA_SYNC(); stage_n<false, 2, 2>(A, nullptr, Y, tile, tid); }
+  }
+  // inverse: rows of Y -> tile (then store_natural); ends with a barrier.  The rows are staged by 16-byte cp.async
+  // (load_rows): reading them inside the first stage (MODE 1, synchronous 8-byte loads per butterfly) was measured
+  // SLOWER (irfft 0.0704 -> 0.0746 ms at B = 64) although it saves a pass over shared memory.
+  BABE_HD static void inverse_from_rows(const float2* Y, float2* A, int tile, int tid) {
+    load_rows(Y, A, tile, tid); PFA_SYNC();
+    stage_n<true, 0, 0>(A, nullptr, nullptr, tile, tid); PFA_SYNC();
+    if (NST > 1) { stage_n<true, 1, 0>(A, nullptr, nullptr, tile, tid); PFA_SYNC(); }
+    if (NST > 2) { stage_n<true, 2, 0>(A, nullptr, nullptr, tile, tid); PFA_SYNC(); }
   }
 };
 
@@ -491,8 +536,7 @@ __global__ void __launch_bounds__(THREADS, PL::MINB1) k_pfa1_fwd(const float2* _
   __syncthreads();
   P::load_natural(x + (size_t)blockIdx.y * PL::NC, A, T1, tile, tid);
   __syncthreads();
-  P::template stages<false>(A, tid);
-  P::store_rows(A, Y + (size_t)blockIdx.y * PL::N1 * PL::P2, tile, tid);
+  P::forward_to_rows(A, Y + (size_t)blockIdx.y * PL::N1 * PL::P2, tile, tid);
 }
 
 template <class PL, int S>
@@ -503,9 +547,7 @@ __global__ void __launch_bounds__(THREADS, PL::MINB1) k_pfa1_inv(const float2* _
   unsigned short* T1 = P::table(A);
   const int tid = threadIdx.x, tile = blockIdx.x;
   P::tables(T1, tid);
-  P::load_rows(Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
-  __syncthreads();
-  P::template stages<true>(A, tid);
+  P::inverse_from_rows(Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
   P::store_natural(A, x + (size_t)blockIdx.y * PL::NC, T1, tile, tid);
 }
 

@@ -47,10 +47,10 @@ static void run(const std::string& dir) {
       unsigned short* T1 = P1::table(A);
       for (int t = 0; t < THREADS; ++t) P1::tables(T1, t);
       for (int t = 0; t < THREADS; ++t) P1::load_natural(in, A, T1, tile, t);
-      for (int t = 0; t < THREADS; ++t) P1::template stage_a<false>(A, t);
-      for (int t = 0; t < THREADS; ++t) P1::template stage_b<false>(A, t);
-      for (int t = 0; t < THREADS; ++t) P1::template stage_c<false>(A, t);
-      for (int t = 0; t < THREADS; ++t) P1::store_rows(A, Yo, tile, t);
+      // the stages of forward_to_rows, barrier by barrier (the last one writes the rows of Y itself)
+      for (int t = 0; t < THREADS; ++t) P1::template stage_n<false, 0, P1::NST == 1 ? 2 : 0>(A, nullptr, Yo, tile, t);
+      for (int t = 0; t < THREADS; ++t) P1::template stage_n<false, 1, P1::NST == 2 ? 2 : 0>(A, nullptr, Yo, tile, t);
+      for (int t = 0; t < THREADS; ++t) P1::template stage_n<false, 2, 2>(A, nullptr, Yo, tile, t);
     }
   };
   auto pass1_inv = [&](const float2* Yi, float2* out) {
@@ -58,10 +58,11 @@ static void run(const std::string& dir) {
       float2* A = reinterpret_cast<float2*>(smem1.data());
       unsigned short* T1 = P1::table(A);
       for (int t = 0; t < THREADS; ++t) P1::tables(T1, t);
+      // the phases of inverse_from_rows
       for (int t = 0; t < THREADS; ++t) P1::load_rows(Yi, A, tile, t);
-      for (int t = 0; t < THREADS; ++t) P1::template stage_a<true>(A, t);
-      for (int t = 0; t < THREADS; ++t) P1::template stage_b<true>(A, t);
-      for (int t = 0; t < THREADS; ++t) P1::template stage_c<true>(A, t);
+      for (int t = 0; t < THREADS; ++t) P1::template stage_n<true, 0, 0>(A, nullptr, nullptr, tile, t);
+      for (int t = 0; t < THREADS; ++t) P1::template stage_n<true, 1, 0>(A, nullptr, nullptr, tile, t);
+      for (int t = 0; t < THREADS; ++t) P1::template stage_n<true, 2, 0>(A, nullptr, nullptr, tile, t);
       for (int t = 0; t < THREADS; ++t) P1::store_natural(A, out, T1, tile, t);
     }
   };
