@@ -80,11 +80,14 @@ struct BandCoreV {
     }
   }
   // z[n1] = input slot TPB n1 + t (times s[n1] if SCALED) -> z[r] = output slot out_slot(r, t)
-  template <bool SCALED>
+  // `after_sync` runs right behind the first band-wide synchronisation: every thread of the band has consumed its
+  // staged inputs by then (the caller re-arms the staging copy for the next row there)
+  template <bool SCALED, class F>
   __device__ static __forceinline__ void fwd(float2 (&z)[16], const float (&s)[16], float2* ex, const float2* tw,
-                                             const Regs& rg, int t, int bar_id) {
+                                             const Regs& rg, int t, int bar_id, F&& after_sync) {
     pass1<SCALED>(z, s, ex, rg, t);
     band_sync<TPB>(bar_id);
+    after_sync();
     pass2(z, ex, t);
     if constexpr (R3 > 1) {
       band_sync<TPB>(bar_id);
@@ -125,11 +128,12 @@ struct BandCoreS {
       for (int k2 = 0; k2 < R2; ++k2) z[j * R2 + k2] = a[k2];
     }
   }
-  template <bool SCALED>
+  template <bool SCALED, class F>
   __device__ static __forceinline__ void fwd(float2 (&z)[16], const float (&s)[16], float2* ex, const float2* tw,
-                                             const Regs& rg, int t, int bar_id) {
+                                             const Regs& rg, int t, int bar_id, F&& after_sync) {
     pass1<SCALED>(z, s, ex, rg, t);
     band_sync<TPB>(bar_id);
+    after_sync();
     pass2(z, ex, t);
   }
 };

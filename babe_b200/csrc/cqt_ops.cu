@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "bandfft.cuh"
 #include "bandfft_v.cuh"
+#include "tma.cuh"
 #include "smemfft.cuh"
 #include "rfft_pairs.cuh"
 #include "cqt_fft.cuh"
@@ -195,6 +196,7 @@ struct BandArgs {
   float2* coef[BABE_MAX_OCTAVES];        // per-octave coefficient tensors [B, binsoct, M] complex
   int planar;                            // 1: float [B, 2, binsoct, M] (re plane, im plane) instead
   int B, rows_per_cta, band_variant;
+  int xpitch;                            // row pitch of X in float2 (Nc + 1, or Nc + 2 when the slices are bulk-copied)
   const int* band_p; const int* band_lg; const int* band_off;
   const float* win; const float* scale;
   const float2* X;                       // analysis: half spectrum [B, Nc+1]
@@ -278,7 +280,7 @@ __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int til
   }
   auto prefetch = [&](int row) {
     if (!SYNTH) {
-      const float2* X = a.X + (size_t)row * (a.Nc + 1) + (p - half);
+      const float2* X = a.X + (size_t)row * a.xpitch + (p - half);
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         int i = C::TPB * n1 + t + half;
@@ -358,18 +360,31 @@ __device__ __forceinline__ void band_tile_fast(const BandArgs& a, int o, int til
 }
 
 // --- octaves with M = 32 ... 4096: packed register FFT (bandfft_v.cuh), 4096 / M bands per CTA (M >= 256) ----------
-// Same data flow as band_tile_fast (next row prefetched with cp.async, window samples in shared memory), but the
-// transform works on float2 register pairs with the two-wide instructions, runs forward or inverse directly (no
+// The transform works on float2 register pairs with the two-wide instructions, runs forward or inverse directly (no
 // conjugations), takes the window (and 1 / M) multiply in its first butterflies, and synchronises per band.
-template <class C, bool SYNTH>
+// Inputs of a row are staged one row ahead:
+//   TMA = true : by the TMA engine -- per band ONE 1-D bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP) of the
+//                contiguous window slice X[p - lg/2 .. p + lg/2) (analysis; start rounded down / length rounded up to
+//                16 bytes, the row pitch of X is even) or of the coefficient row (synthesis; two copies for the planar
+//                layout), issued by one thread per synchronisation group right behind the band's first barrier;
+//                no per-thread address / predicate / LDGSTS work in the row loop;
+//   TMA = false: by 16 8-byte cp.async per thread (round 2, first session): any alignment / pitch.
+template <class C, bool SYNTH, bool TMA>
 __device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, int row0, int row_end,
                                             unsigned char* smem_raw) {
   constexpr int NB = BAND_THREADS / C::TPB, M = C::M, NTWP = (C::NTW + 1) & ~1;
+  constexpr int GT = C::TPB < 32 ? 32 : C::TPB;            // threads per synchronisation group (>= one warp)
+  constexpr int NG = BAND_THREADS / GT, BPG = GT / C::TPB; // groups per CTA, bands per group
+  constexpr int SB = M + 2;                                // staged float2 per band (TMA): slice + alignment pads
+  constexpr int STAGE = TMA ? NB * SB : 16 * BAND_THREADS;
   float2* exs = reinterpret_cast<float2*>(smem_raw);
   float2* tw = exs + ((NB * C::EXP + 1) & ~1);
-  float2* stage = tw + NTWP;                           // [16][BAND_THREADS]: input slot n1 of thread tid
-  float* wst = reinterpret_cast<float*>(stage + 16 * BAND_THREADS);
-  const int tid = threadIdx.x, bl = tid / C::TPB, t = tid % C::TPB;
+  float2* stage = tw + NTWP;                           // TMA: [NB][SB] natural order; else [16][BAND_THREADS]
+  float* wst = reinterpret_cast<float*>(stage + STAGE);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wst + 16 * BAND_THREADS);      // [NG]
+  int* s_src = reinterpret_cast<int*>(mbar + NG);      // [NB] first staged element of the band's slice (analysis)
+  int* s_cnt = s_src + NB;                             // [NB] staged elements
+  const int tid = threadIdx.x, bl = tid / C::TPB, t = tid % C::TPB, grp = tid / GT;
   const float2* roots_m = a.rootsm[o];
   for (int i = tid; i < C::NTW; i += BAND_THREADS) tw[i] = C::twiddle(roots_m, i);
   typename C::Regs rg;
@@ -383,7 +398,9 @@ __device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, 
   }
   const int half = lg / 2;
   float2* ex = exs + bl * C::EXP;
+  float2* stage_b = stage + bl * SB;
   unsigned valid = 0;
+  int sdelta = 0;                                      // TMA analysis: stage index of window sample i is i + sdelta
   if (!SYNTH) {
     // window sample (times the optional bin scale and 1 / M) of the thread's 16 INPUT slots; 0 = outside the window
     const float inv_m = 1.0f / (float)M;
@@ -399,7 +416,15 @@ __device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, 
         valid |= 1u << n1;
       }
       wst[n1 * BAND_THREADS + tid] = w;
-      stage[n1 * BAND_THREADS + tid] = make_float2(0.f, 0.f);
+      if (!TMA) stage[n1 * BAND_THREADS + tid] = make_float2(0.f, 0.f);
+    }
+    if (TMA) {
+      // slice [kstart, kend) of the row, widened to 16-byte boundaries; staged slots outside it keep their zeros
+      const int start = p - half, kstart = max(start, 0), kend = min(start + lg, a.Nc + 1);
+      const int s0 = kstart & ~1, cnt = active && kend > s0 ? ((kend - s0 + 1) & ~1) : 0;
+      sdelta = start - s0;
+      if (t == 0) { s_src[bl] = s0; s_cnt[bl] = cnt; }
+      for (int i = t; i < SB; i += C::TPB) stage_b[i] = make_float2(0.f, 0.f);
     }
   } else {
     // dual-window sample of the thread's 16 OUTPUT slots
@@ -409,10 +434,39 @@ __device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, 
       if (i >= M) i -= M;
       wst[r * BAND_THREADS + tid] = (active && i < lg) ? a.win[off + i] : 0.f;
     }
+    if (TMA && t == 0) { s_src[bl] = band; s_cnt[bl] = active ? M : 0; }
   }
+  if (TMA && tid < NG) tma::mbar_init(mbar + tid, 1);
+  if (TMA) tma::fence_proxy_async();                   // zeros / barrier inits before the first bulk copy
+  // ---- staging of one row ------------------------------------------------------------------------------
   auto prefetch = [&](int row) {
+    if (TMA) {
+      if (tid % GT != 0) return;                       // one thread per synchronisation group
+      uint64_t* bar = mbar + grp;
+      unsigned total = 0;
+#pragma unroll
+      for (int b = 0; b < BPG; ++b) total += (unsigned)s_cnt[grp * BPG + b] * 8u;
+      if (total == 0) { tma::mbar_arrive(bar); return; }
+      tma::mbar_arrive_tx(bar, total);
+#pragma unroll
+      for (int b = 0; b < BPG; ++b) {
+        const int bb = grp * BPG + b, cnt = s_cnt[bb];
+        if (cnt == 0) continue;
+        float2* dst = stage + bb * SB;
+        if (!SYNTH) {
+          tma::bulk_g2s(dst, a.X + (size_t)row * a.xpitch + s_src[bb], cnt * 8u, bar);
+        } else if (!a.planar) {
+          tma::bulk_g2s(dst, a.coef[o] + ((size_t)row * a.binsoct + s_src[bb]) * M, cnt * 8u, bar);
+        } else {
+          const float* ire = reinterpret_cast<const float*>(a.coef[o]) + (((size_t)row * 2) * a.binsoct + s_src[bb]) * M;
+          tma::bulk_g2s(dst, ire, cnt * 4u, bar);                                          // real plane -> floats [0, M)
+          tma::bulk_g2s(reinterpret_cast<float*>(dst) + M, ire + (size_t)a.binsoct * M, cnt * 4u, bar);   // imaginary
+        }
+      }
+      return;
+    }
     if (!SYNTH) {
-      const float2* X = a.X + (size_t)row * (a.Nc + 1) + (p - half);
+      const float2* X = a.X + (size_t)row * a.xpitch + (p - half);
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         int i = C::in_slot(n1, t) + half;
@@ -436,25 +490,50 @@ __device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, 
       }
     }
   };
+  if (TMA) __syncthreads();                            // barrier inits, slice descriptors, zeroed stage
   if (row0 < row_end) prefetch(row0);
-  __syncthreads();                                  // twiddle table
+  __syncthreads();                                     // twiddle table
+  unsigned phase = 0;
   for (int row = row0; row < row_end; ++row) {
     float2 z[16];
     float s[16];
-    cp_async_commit_wait();                         // this thread's own copies: no barrier needed to read them
-    if (SYNTH && !active) {
+    if (TMA) {
+      tma::mbar_wait(mbar + grp, phase);
+      phase ^= 1u;
+      if (!SYNTH) {
 #pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) z[n1] = make_float2(0.f, 0.f);
+        for (int n1 = 0; n1 < 16; ++n1) {
+          int i = C::in_slot(n1, t) + half;
+          if (i >= M) i -= M;
+          i = min(max(i + sdelta, 0), SB - 1);           // slots outside the slice carry weight 0
+          z[n1] = stage_b[i];
+        }
+      } else if (!a.planar) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) z[n1] = active ? stage_b[C::in_slot(n1, t)] : make_float2(0.f, 0.f);
+      } else {
+        const float* sf = reinterpret_cast<const float*>(stage_b);
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1)
+          z[n1] = active ? make_float2(sf[C::in_slot(n1, t)], sf[M + C::in_slot(n1, t)]) : make_float2(0.f, 0.f);
+      }
     } else {
+      cp_async_commit_wait();                         // this thread's own copies: no barrier needed to read them
+      if (SYNTH && !active) {
 #pragma unroll
-      for (int n1 = 0; n1 < 16; ++n1) z[n1] = stage[n1 * BAND_THREADS + tid];
+        for (int n1 = 0; n1 < 16; ++n1) z[n1] = make_float2(0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) z[n1] = stage[n1 * BAND_THREADS + tid];
+      }
     }
     if (!SYNTH) {
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) s[n1] = wst[n1 * BAND_THREADS + tid];
     }
-    if (row + 1 < row_end) prefetch(row + 1);       // the staged values are in registers: the slots are free
-    C::template fwd<!SYNTH>(z, s, ex, tw, rg, t, 1 + bl);
+    const bool more = row + 1 < row_end;
+    if (!TMA && more) prefetch(row + 1);              // the staged values are in registers: the slots are free
+    C::template fwd<!SYNTH>(z, s, ex, tw, rg, t, 1 + bl, [&]() { if (TMA && more) prefetch(row + 1); });
     if (active) {
       if (!SYNTH) {
         if (!a.planar) {
@@ -507,7 +586,7 @@ __device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int 
   const float inv_m = 1.0f / (float)M;
   for (int row = row0; row < row_end; ++row) {
     if (!SYNTH) {
-      const float2* X = a.X + (size_t)row * (a.Nc + 1);
+      const float2* X = a.X + (size_t)row * a.xpitch;
 #pragma unroll 4
       for (int idx = tid; idx < nb * M; idx += nthr) {
         const int bl = idx >> mshift, m = idx & (M - 1);
@@ -583,7 +662,7 @@ __device__ __forceinline__ void band_tile_generic(const BandArgs& a, int o, int 
 
 // V: packed per-band cores (bandfft_v.cuh, default) / round 2's cores (A/B: babe_set_cqt_band_variant(0)).  Separate
 // kernels: one body with both sets inlined is 32 K SASS instructions.
-template <bool SYNTH, bool V>
+template <bool SYNTH, bool V, bool TMA>
 __device__ __forceinline__ void band_segment(const BandArgs& a, int o, int tile, int row0, int row_end,
                                              unsigned char* smem_raw) {
   if (!V) {
@@ -598,19 +677,19 @@ __device__ __forceinline__ void band_segment(const BandArgs& a, int o, int tile,
     return;
   }
   switch (a.M[o]) {                  // analysis = inverse transform of the windowed slice, synthesis = forward
-    case 32: band_tile_v<BandCoreS<2, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
-    case 64: band_tile_v<BandCoreS<4, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
-    case 128: band_tile_v<BandCoreS<8, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
-    case 256: band_tile_v<BandCoreV<1, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
-    case 512: band_tile_v<BandCoreV<2, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
-    case 1024: band_tile_v<BandCoreV<4, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
-    case 2048: band_tile_v<BandCoreV<8, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
-    case 4096: band_tile_v<BandCoreV<16, !SYNTH>, SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    case 32: band_tile_v<BandCoreS<2, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
+    case 64: band_tile_v<BandCoreS<4, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
+    case 128: band_tile_v<BandCoreS<8, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
+    case 256: band_tile_v<BandCoreV<1, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
+    case 512: band_tile_v<BandCoreV<2, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
+    case 1024: band_tile_v<BandCoreV<4, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
+    case 2048: band_tile_v<BandCoreV<8, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
+    case 4096: band_tile_v<BandCoreV<16, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
     default: band_tile_generic<SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
   }
 }
 
-template <bool SYNTH, bool V>
+template <bool SYNTH, bool V, bool TMA>
 __device__ __forceinline__ void band_tile(const BandArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o = find_octave(a, blockIdx.x);
@@ -618,16 +697,19 @@ __device__ __forceinline__ void band_tile(const BandArgs& a) {
   if (SYNTH && blockIdx.x == 0 && threadIdx.x < 2)          // the "no band" entries of the rows (a.sum_lg = pitch)
     for (int row = row0; row < row_end; ++row)
       a.BS[(size_t)row * a.sum_lg + a.sum_lg - 2 + threadIdx.x] = make_float2(0.f, 0.f);
-  band_segment<SYNTH, V>(a, o, blockIdx.x - a.tile0[o], row0, row_end, smem_raw);
+  band_segment<SYNTH, V, TMA>(a, o, blockIdx.x - a.tile0[o], row0, row_end, smem_raw);
 }
 
 // analysis: window multiply + fold + per-band inverse FFT of the half spectrum X
-__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_analysis(const BandArgs a) { band_tile<false, true>(a); }
 // synthesis, first half: per-band FFT of the coefficients, dual-window multiply -> band spectra BS
-__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_synth_bands(const BandArgs a) { band_tile<true, true>(a); }
+// TMA: inputs staged by bulk copies (default); the cp.async variants serve misaligned inputs and the A/B knob
+template <bool TMA>
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_analysis(const BandArgs a) { band_tile<false, true, TMA>(a); }
+template <bool TMA>
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_synth_bands(const BandArgs a) { band_tile<true, true, TMA>(a); }
 // the same on round 2's cores
-__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_analysis_r2(const BandArgs a) { band_tile<false, false>(a); }
-__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_synth_bands_r2(const BandArgs a) { band_tile<true, false>(a); }
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_analysis_r2(const BandArgs a) { band_tile<false, false, false>(a); }
+__global__ void __launch_bounds__(BAND_THREADS, 2) k_cqt_synth_bands_r2(const BandArgs a) { band_tile<true, false, false>(a); }
 
 // overlap-add of the band spectra as a gather, fused with the c2r pre-processing
 struct GatherArgs {
@@ -819,15 +901,16 @@ struct PfaRun {
     pfa::P2Args a{};
     a.tw_ls = reinterpret_cast<const float2*>(p->tw_ls);
     a.scale = scale;
+    a.xpitch = PL::NC + 1;
     return a;
   }
   // x[B, Ls] -> X[B, Nc + 1] * scale
   static int rfft(const babe_cqt_plan* p, const float2* x, float2* tmp, float2* X, const float* scale, int B,
-                  cudaStream_t st) {
+                  int xpitch, cudaStream_t st) {
     int rc = pass1_fwd(x, tmp, B, st);
     if (rc) return rc;
     pfa::P2Args a = args(p, scale);
-    a.Y = tmp; a.Xout = X;
+    a.Y = tmp; a.Xout = X; a.xpitch = xpitch;
     cudaFuncSetAttribute(pfa::k_pfa2_fwd<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
     pfa::k_pfa2_fwd<PL, PFA_S><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
     return check_launch("k_pfa2_fwd");
@@ -880,8 +963,8 @@ struct PfaRun {
     }                                                                                             \
   } while (0)
 static int pfa_rfft(const babe_cqt_plan* p, const float2* x, float2* tmp, float2* X, const float* scale, int B,
-                    cudaStream_t st) {
-  BABE_PFA_DISPATCH(rfft(p, x, tmp, X, scale, B, st));
+                    int xpitch, cudaStream_t st) {
+  BABE_PFA_DISPATCH(rfft(p, x, tmp, X, scale, B, xpitch, st));
 }
 static int pfa_irfft(const babe_cqt_plan* p, const float2* X, const float2* BS, float2* tmp, float2* x,
                      const float* scale, int B, cudaStream_t st) {
@@ -979,7 +1062,8 @@ static int tiled_irfft(const babe_cqt_plan* p, const float2* X, const float2* BS
   return launch_f1(p, tmp, x, B, 0, 1, st);
 }
 
-// 1 (default): packed band cores (bandfft_v.cuh); 0: round 2's BandCore / generic Stockham
+// 1 (default): packed band cores (bandfft_v.cuh), analysis slices staged by TMA bulk copies, synthesis rows by
+// cp.async; 2: cp.async for both; 3: TMA for both; 0: round 2's BandCore / generic Stockham
 static int g_band_variant = 1;
 static inline int band_r3(int M) {     // M = 256 * R3 handled by BandCore<R3>, else 0
   switch (M) { case 256: return 1; case 512: return 2; case 1024: return 4; case 2048: return 8;
@@ -999,12 +1083,12 @@ static int fill_band_args(const babe_cqt_plan* p, BandArgs& a, size_t& smem, int
     if (g_band_variant != 0 && (M == 32 || M == 64 || M == 128)) {   // BandCoreS<R2>: R2 threads per band
       const int r2 = M / 16;
       tb = BAND_THREADS / r2;
-      need = sizeof(float2) * ((size_t)((tb * (16 * (r2 + 1) + r2) + 1) & ~1) + 2 + 16 * BAND_THREADS) +
-             sizeof(float) * 16 * BAND_THREADS;
+      need = sizeof(float2) * ((size_t)((tb * (16 * (r2 + 1) + r2) + 1) & ~1) + 2 + 16 * BAND_THREADS + 2 * tb) +
+             sizeof(float) * 16 * BAND_THREADS + 64 + 8 * tb;   // + TMA: slice pads, mbarriers, slice descriptors
     } else if (r3) {                           // register FFT: 4096 points per CTA
       tb = 16 / r3;
-      need = sizeof(float2) * ((size_t)tb * 16 * (16 * r3 + 1) + 16 * r3 + 16 * BAND_THREADS) +
-             sizeof(float) * 16 * BAND_THREADS;   // ex + twiddles + prefetch stage + window samples
+      need = sizeof(float2) * ((size_t)tb * 16 * (16 * r3 + 1) + 16 * r3 + 16 * BAND_THREADS + 2 * tb) +
+             sizeof(float) * 16 * BAND_THREADS + 64 + 8 * tb;   // ex + twiddles + stage + window samples (+ TMA extras)
     } else {                                   // shared-memory Stockham: <= 2048 points per CTA
       tb = std::max(1, std::min(std::min(p->binsoct, MAX_TB), 2048 / M));
       need = sizeof(float2) * ((size_t)2 * tb * odd_stride(M) + M);
@@ -1046,7 +1130,8 @@ extern "C" int babe_rfft(const babe_cqt_plan* plan, const float* x, float* X, in
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pfa_id(plan))
-    return pfa_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, reinterpret_cast<float2*>(X), bin_scale, B, st);
+    return pfa_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, reinterpret_cast<float2*>(X), bin_scale, B,
+                    plan->Nc + 1, st);
   if (tiled_ok(plan))
     return tiled_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, reinterpret_cast<float2*>(X), bin_scale, B, st);
   rc = big_fft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufB, B, 0, st);
@@ -1122,8 +1207,10 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
   rc = carve(plan, B, workspace, workspace_bytes, w);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int xpitch = plan->Nc + 1;
   if (pfa_id(plan)) {
-    rc = pfa_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufX, nullptr, B, st);
+    xpitch = plan->Nc + 2;       // even: rows of the internal spectrum are 16-byte aligned (bulk-copied slices)
+    rc = pfa_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufX, nullptr, B, xpitch, st);
     if (rc) return rc;
   } else if (tiled_ok(plan)) {
     rc = tiled_rfft(plan, reinterpret_cast<const float2*>(x), w.bufA, w.bufX, nullptr, B, st);
@@ -1146,11 +1233,17 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
     BABE_REQUIRE(out_octaves_host[o] != nullptr, BABE_EBADARG, "cqt_analysis: null octave %d", o);
     a.coef[o] = reinterpret_cast<float2*>(out_octaves_host[o]);
   }
-  a.win = win; a.scale = bin_scale; a.X = w.bufX; a.planar = planar ? 1 : 0;
+  a.win = win; a.scale = bin_scale; a.X = w.bufX; a.planar = planar ? 1 : 0; a.xpitch = xpitch;
   const dim3 grid(items, (B + a.rows_per_cta - 1) / a.rows_per_cta);
-  if (a.band_variant) {
-    cudaFuncSetAttribute(k_cqt_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cqt_analysis<<<grid, BAND_THREADS, smem, st>>>(a);
+  // bulk-copied window slices need 16-byte aligned rows of X: the internal spectrum buffer of the prime-factor path
+  const bool tma_ok = (a.band_variant == 1 || a.band_variant == 3) && (a.xpitch % 2 == 0) &&
+                      (reinterpret_cast<uintptr_t>(a.X) % 16 == 0);
+  if (tma_ok) {
+    cudaFuncSetAttribute(k_cqt_analysis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cqt_analysis<true><<<grid, BAND_THREADS, smem, st>>>(a);
+  } else if (a.band_variant) {
+    cudaFuncSetAttribute(k_cqt_analysis<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cqt_analysis<false><<<grid, BAND_THREADS, smem, st>>>(a);
   } else {
     cudaFuncSetAttribute(k_cqt_analysis_r2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_cqt_analysis_r2<<<grid, BAND_THREADS, smem, st>>>(a);
@@ -1179,9 +1272,17 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
   }
   a.win = win; a.scale = nullptr; a.BS = w.bufS; a.planar = planar ? 1 : 0;
   const dim3 grid(items, (B + a.rows_per_cta - 1) / a.rows_per_cta);
-  if (a.band_variant) {
-    cudaFuncSetAttribute(k_cqt_synth_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cqt_synth_bands<<<grid, BAND_THREADS, smem, st>>>(a);
+  // bulk-copied coefficient rows (16-byte aligned octave tensors) only on request (variant 3): measured against the
+  // cp.async staging, 68.3 vs 69.8 us at B = 64 but 18.2 vs 16.2 us at B = 8 and 20.2 vs 17.1 us for the planar layout
+  // the sampler uses (two copies per band) -- profiles/r02_cqt.md
+  bool tma_ok = a.band_variant == 3;
+  for (int o = 0; o < plan->numocts; ++o) tma_ok = tma_ok && reinterpret_cast<uintptr_t>(a.coef[o]) % 16 == 0;
+  if (tma_ok) {
+    cudaFuncSetAttribute(k_cqt_synth_bands<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cqt_synth_bands<true><<<grid, BAND_THREADS, smem, st>>>(a);
+  } else if (a.band_variant) {
+    cudaFuncSetAttribute(k_cqt_synth_bands<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cqt_synth_bands<false><<<grid, BAND_THREADS, smem, st>>>(a);
   } else {
     cudaFuncSetAttribute(k_cqt_synth_bands_r2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_cqt_synth_bands_r2<<<grid, BAND_THREADS, smem, st>>>(a);
@@ -1212,7 +1313,7 @@ extern "C" int babe_set_cqt_variant(int v) {
 }
 extern "C" int babe_get_cqt_variant(void) { return babe::g_cqt_variant; }
 extern "C" int babe_set_cqt_band_variant(int v) {
-  if (v < 0 || v > 1) return BABE_EBADARG;
+  if (v < 0 || v > 3) return BABE_EBADARG;
   babe::g_band_variant = v;
   return BABE_OK;
 }

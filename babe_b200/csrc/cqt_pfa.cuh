@@ -561,6 +561,7 @@ struct P2Args {
   int sum_lg;
   const float2* tw_ls;
   const float* scale;      // optional bin scale / the filter H
+  int xpitch;              // row pitch of X / Xout in float2 (>= Nc + 1; Nc + 2: 16-byte rows, pad element zeroed)
 };
 
 // forward pass 2 + r2c -> X
@@ -575,7 +576,9 @@ __global__ void __launch_bounds__(THREADS, PL::MINB2) k_pfa2_fwd(const P2Args a)
   P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
   __syncthreads();
   P::template stages<false>(A, tile, tid);
-  P::post_to_x(A, a.Xout + (size_t)blockIdx.y * (PL::NC + 1), a.tw_ls, a.scale, tile, tid);
+  float2* Xrow = a.Xout + (size_t)blockIdx.y * a.xpitch;
+  P::post_to_x(A, Xrow, a.tw_ls, a.scale, tile, tid);
+  if (tile == 0 && tid == 0 && a.xpitch > PL::NC + 1) Xrow[PL::NC + 1] = make_float2(0.f, 0.f);   // pad: staged by bulk copies
 }
 
 // forward pass 2, r2c, * H, c2r, inverse pass 2 (apply_hpf_DC)
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(THREADS, PL::MINB2) k_pfa2_inv(const P2Args a)
   P::tables(A, a.tw_ls, tid);
   __syncthreads();
   GatherTab g{GATHER ? a.BS + (size_t)blockIdx.y * a.sum_lg : nullptr, a.src};
-  P::template pre_from_x<GATHER>(A, GATHER ? nullptr : a.X + (size_t)blockIdx.y * (PL::NC + 1), g, a.tw_ls, a.scale,
+  P::template pre_from_x<GATHER>(A, GATHER ? nullptr : a.X + (size_t)blockIdx.y * a.xpitch, g, a.tw_ls, a.scale,
                                  tile, tid);
   __syncthreads();
   P::template stages<true>(A, tile, tid);

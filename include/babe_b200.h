@@ -83,7 +83,10 @@ int babe_get_fused_variant(void);
 int babe_set_cqt_variant(int variant);
 int babe_get_cqt_variant(void);
 /* Band kernels of babe_cqt_analysis / babe_cqt_synthesis: 1 (default) packed register FFTs with per-band
- * synchronisation for every octave size 32 ... 4096 (csrc/bandfft_v.cuh); 0: round 2's cores (A/B). */
+ * synchronisation for every octave size 32 ... 4096 (csrc/bandfft_v.cuh); the analysis stages each band's window slice
+ * of the spectrum with one TMA bulk copy per row, the synthesis its coefficient rows with cp.async (faster at the
+ * sampler's batch and planar layout); 2: cp.async staging for both (also serves misaligned inputs); 3: TMA staging
+ * for both; 0: round 2's cores (A/B). */
 int babe_set_cqt_band_variant(int variant);
 
 /* ---- a3/a12: fused STFT -> H -> iSTFT ---------------------------------- */

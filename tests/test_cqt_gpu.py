@@ -166,22 +166,28 @@ def test_tiled_passes_vs_oracle(CQT, variant, numocts, binsoct, fs, Ls, B):
         lib().babe_set_cqt_variant(2)
 
 
+@pytest.mark.parametrize("band_variant", [0, 2, 3])
 @pytest.mark.parametrize("numocts,binsoct,fs,Ls,B", [(7, 64, 22050, 184184, 2), (4, 12, 22050, 8192, 3)])
-def test_round2_band_cores_vs_oracle(CQT, numocts, binsoct, fs, Ls, B):
-    """`babe_set_cqt_band_variant(0)`: round 2's band kernels (BandCore on split re / im registers, CTA-wide barriers,
-    generic Stockham for the octaves below 256 points), kept for A/B against the packed per-band cores of
-    csrc/bandfft_v.cuh that every other test runs."""
+def test_other_band_kernels_vs_oracle(CQT, band_variant, numocts, binsoct, fs, Ls, B):
+    """`babe_set_cqt_band_variant`: 0 = round 2's band kernels (BandCore on split re / im registers, CTA-wide barriers,
+    generic Stockham for the octaves below 256 points); 2 / 3 = the packed per-band cores of csrc/bandfft_v.cuh with
+    cp.async / TMA bulk-copy staging on BOTH directions (the default, 1, stages the analysis slices by TMA and the
+    synthesis rows by cp.async and is what every other test runs).  Complex and planar layouts."""
     from babe_b200._lib import lib
     cq, ref = _pair(CQT, numocts, binsoct, fs, Ls)
     g = torch.Generator().manual_seed(Ls + 2)
     x = torch.randn(B, Ls, generator=g) * 0.063
     xc = x.cuda()
-    assert lib().babe_set_cqt_band_variant(0) == 0
+    assert lib().babe_set_cqt_band_variant(band_variant) == 0
     try:
         c = cq.fwd(xc.unsqueeze(1))
         cr = ref.fwd(x.double())
         for o in range(numocts):
             assert rel_l2(torch.view_as_real(c[o].cpu().squeeze(1)), torch.view_as_real(cr[o])) < TOL, o
         assert rel_l2(cq.bwd(c).cpu().squeeze(1), ref.bwd(cr)) < TOL
+        cp = cq.fwd_planar(xc)
+        for o in range(numocts):
+            assert rel_l2(cp[o].permute(0, 2, 3, 1).cpu(), torch.view_as_real(cr[o]).float()) < TOL, o
+        assert rel_l2(cq.bwd_planar(cp).cpu(), ref.bwd(cr)) < TOL
     finally:
         lib().babe_set_cqt_band_variant(1)
