@@ -28,7 +28,9 @@ print("Static instruction counts per kernel.  FFMA2 / FADD2 / FMUL2: Blackwell t
 print("**UBLKCP: 1-D bulk TMA copy (`cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes`), SYNCS: its mbarrier**")
 print("(init / arrive.expect_tx / try_wait) -- the frame tiles of the fused NFFT-4096 operators (`k_filter_fused`, `k_stats_fused`,")
 print("`k_fir_fused`, csrc/stft_fused.cu) are staged by the TMA engine; the round-1 kernels they replace (`k_apply_filter<Core3,1>`,")
-print("`k_stft_stats<Core3,1>`, `k_fir_filter<Core3>`) remain as the path for rows that cannot be bulk-copied.  No tensor-core")
+print("`k_stft_stats<Core3,1>`, `k_fir_filter<Core3>`) remain as the path for rows that cannot be bulk-copied; `k_cqt_analysis<true>`")
+print("stages each band's window slice of the spectrum the same way.  The prime-factor passes of the CQT (`pfa::k_pfa*`,")
+print("csrc/cqt_pfa.cuh) and the band cores (csrc/bandfft_v.cuh) run on the two-wide instructions.  No tensor-core")
 print("instructions (north star: not a dense contraction).\n")
 print("| kernel | instructions | " + " | ".join(cols) + " | fp64 |")
 print("|---|---:|" + "---:|" * (len(cols) + 1))
