@@ -491,6 +491,7 @@ __device__ __forceinline__ void band_tile_v(const BandArgs& a, int o, int tile, 
     }
   };
   if (TMA) __syncthreads();                            // barrier inits, slice descriptors, zeroed stage
+  pfa::pdl_wait();                                     // everything above read plan constants only
   if (row0 < row_end) prefetch(row0);
   __syncthreads();                                     // twiddle table
   unsigned phase = 0;
@@ -685,19 +686,21 @@ __device__ __forceinline__ void band_segment(const BandArgs& a, int o, int tile,
     case 1024: band_tile_v<BandCoreV<4, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
     case 2048: band_tile_v<BandCoreV<8, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
     case 4096: band_tile_v<BandCoreV<16, !SYNTH>, SYNTH, TMA>(a, o, tile, row0, row_end, smem_raw); break;
-    default: band_tile_generic<SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
+    default: pfa::pdl_wait(); band_tile_generic<SYNTH>(a, o, tile, row0, row_end, smem_raw); break;
   }
 }
 
 template <bool SYNTH, bool V, bool TMA>
 __device__ __forceinline__ void band_tile(const BandArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pfa::pdl_launch_dependents();
   const int o = find_octave(a, blockIdx.x);
   const int row0 = blockIdx.y * a.rows_per_cta, row_end = min(a.B, row0 + a.rows_per_cta);
+  if (!V) pfa::pdl_wait();                                  // the packed tiles wait behind their own preamble
+  band_segment<SYNTH, V, TMA>(a, o, blockIdx.x - a.tile0[o], row0, row_end, smem_raw);
   if (SYNTH && blockIdx.x == 0 && threadIdx.x < 2)          // the "no band" entries of the rows (a.sum_lg = pitch)
     for (int row = row0; row < row_end; ++row)
       a.BS[(size_t)row * a.sum_lg + a.sum_lg - 2 + threadIdx.x] = make_float2(0.f, 0.f);
-  band_segment<SYNTH, V, TMA>(a, o, blockIdx.x - a.tile0[o], row0, row_end, smem_raw);
 }
 
 // analysis: window multiply + fold + per-band inverse FFT of the half spectrum X
@@ -867,6 +870,20 @@ static bool tiled_ok(const babe_cqt_plan* p) {
          tile_fft_smem(p->f2.n) <= 220 * 1024;
 }
 
+// ---- programmatic dependent launch of the kernels of a CQT chain (device side: cqt_pfa.cuh) -------------------------
+static int g_cqt_pdl = 7;      // bit mask, A/B: babe_set_cqt_pdl (1: pass-1 kernels, 2: pass-2 kernels, 4: band kernels,
+                               // 8: the gathering inverse pass 2 behind the synthesis band kernel -- off by default)
+template <int KIND, class... KArgs, class... Args>
+static void launch_chain(void (*kern)(KArgs...), dim3 grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (g_cqt_pdl & KIND) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- third-generation length-Ls transform: prime-factor passes (cqt_pfa.cuh) -----------------------------------
 using Pfa92092 = pfa::Plan<4, 7, 11, 13, 23, 1>;      // Ls = 184184: 22.05 kHz x 8.35 s (BASELINE configs[1])
 using Pfa184184 = pfa::Plan<8, 7, 11, 13, 23, 1>;     // Ls = 368368: 44.1 kHz x 8.35 s (conf/exp/maestro44k_8s.yaml)
@@ -889,12 +906,12 @@ struct PfaRun {
   using P2 = pfa::Pass2<PL, PFA_S>;
   static int pass1_fwd(const float2* x, float2* Y, int B, cudaStream_t st) {
     cudaFuncSetAttribute(pfa::k_pfa1_fwd<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1::SMEM);
-    pfa::k_pfa1_fwd<PL, PFA_S><<<dim3(P1::TILES, B), pfa::THREADS, P1::SMEM, st>>>(x, Y);
+    launch_chain<1>(pfa::k_pfa1_fwd<PL, PFA_S>, dim3(P1::TILES, B), pfa::THREADS, P1::SMEM, st, x, Y);
     return check_launch("k_pfa1_fwd");
   }
   static int pass1_inv(const float2* Y, float2* x, int B, cudaStream_t st) {
     cudaFuncSetAttribute(pfa::k_pfa1_inv<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1::SMEM);
-    pfa::k_pfa1_inv<PL, PFA_S><<<dim3(P1::TILES, B), pfa::THREADS, P1::SMEM, st>>>(Y, x);
+    launch_chain<1>(pfa::k_pfa1_inv<PL, PFA_S>, dim3(P1::TILES, B), pfa::THREADS, P1::SMEM, st, Y, x);
     return check_launch("k_pfa1_inv");
   }
   static pfa::P2Args args(const babe_cqt_plan* p, const float* scale) {
@@ -912,7 +929,7 @@ struct PfaRun {
     pfa::P2Args a = args(p, scale);
     a.Y = tmp; a.Xout = X; a.xpitch = xpitch;
     cudaFuncSetAttribute(pfa::k_pfa2_fwd<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
-    pfa::k_pfa2_fwd<PL, PFA_S><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
+    launch_chain<2>(pfa::k_pfa2_fwd<PL, PFA_S>, dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st, a);
     return check_launch("k_pfa2_fwd");
   }
   // X[B, Nc + 1] * scale (or the gathered band spectra) -> x[B, Ls]
@@ -923,10 +940,12 @@ struct PfaRun {
     if (BS != nullptr) {
       a.BS = BS; a.src = reinterpret_cast<const int4*>(p->bin_src); a.sum_lg = bs_pitch(p);
       cudaFuncSetAttribute(pfa::k_pfa2_inv<PL, PFA_S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
-      pfa::k_pfa2_inv<PL, PFA_S, true><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
+      // behind the band kernel (128 registers, one wave) an early start of this kernel measured SLOWER (synthesis
+      // 0.155 -> 0.178 ms at B = 64, 0.038 -> 0.044 ms at B = 8): plain stream order for this one edge
+      launch_chain<8>(pfa::k_pfa2_inv<PL, PFA_S, true>, dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st, a);
     } else {
       cudaFuncSetAttribute(pfa::k_pfa2_inv<PL, PFA_S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
-      pfa::k_pfa2_inv<PL, PFA_S, false><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
+      launch_chain<2>(pfa::k_pfa2_inv<PL, PFA_S, false>, dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st, a);
     }
     int rc = check_launch("k_pfa2_inv");
     if (rc) return rc;
@@ -940,7 +959,7 @@ struct PfaRun {
     pfa::P2Args a = args(p, H);
     a.Y = tmpA; a.Yout = tmpB;
     cudaFuncSetAttribute(pfa::k_pfa2_mid<PL, PFA_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
-    pfa::k_pfa2_mid<PL, PFA_S><<<dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st>>>(a);
+    launch_chain<2>(pfa::k_pfa2_mid<PL, PFA_S>, dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st, a);
     rc = check_launch("k_pfa2_mid");
     if (rc) return rc;
     return pass1_inv(tmpB, y, B, st);
@@ -1240,13 +1259,13 @@ extern "C" int babe_cqt_analysis(const babe_cqt_plan* plan, const float* x,
                       (reinterpret_cast<uintptr_t>(a.X) % 16 == 0);
   if (tma_ok) {
     cudaFuncSetAttribute(k_cqt_analysis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cqt_analysis<true><<<grid, BAND_THREADS, smem, st>>>(a);
+    launch_chain<4>(k_cqt_analysis<true>, grid, BAND_THREADS, smem, st, a);
   } else if (a.band_variant) {
     cudaFuncSetAttribute(k_cqt_analysis<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cqt_analysis<false><<<grid, BAND_THREADS, smem, st>>>(a);
+    launch_chain<4>(k_cqt_analysis<false>, grid, BAND_THREADS, smem, st, a);
   } else {
     cudaFuncSetAttribute(k_cqt_analysis_r2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cqt_analysis_r2<<<grid, BAND_THREADS, smem, st>>>(a);
+    launch_chain<4>(k_cqt_analysis_r2, grid, BAND_THREADS, smem, st, a);
   }
   return check_launch("k_cqt_analysis");
 }
@@ -1279,13 +1298,13 @@ extern "C" int babe_cqt_synthesis(const babe_cqt_plan* plan, const float* const*
   for (int o = 0; o < plan->numocts; ++o) tma_ok = tma_ok && reinterpret_cast<uintptr_t>(a.coef[o]) % 16 == 0;
   if (tma_ok) {
     cudaFuncSetAttribute(k_cqt_synth_bands<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cqt_synth_bands<true><<<grid, BAND_THREADS, smem, st>>>(a);
+    launch_chain<4>(k_cqt_synth_bands<true>, grid, BAND_THREADS, smem, st, a);
   } else if (a.band_variant) {
     cudaFuncSetAttribute(k_cqt_synth_bands<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cqt_synth_bands<false><<<grid, BAND_THREADS, smem, st>>>(a);
+    launch_chain<4>(k_cqt_synth_bands<false>, grid, BAND_THREADS, smem, st, a);
   } else {
     cudaFuncSetAttribute(k_cqt_synth_bands_r2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cqt_synth_bands_r2<<<grid, BAND_THREADS, smem, st>>>(a);
+    launch_chain<4>(k_cqt_synth_bands_r2, grid, BAND_THREADS, smem, st, a);
   }
   rc = check_launch("k_cqt_synth_bands");
   if (rc) return rc;
@@ -1312,6 +1331,10 @@ extern "C" int babe_set_cqt_variant(int v) {
   return BABE_OK;
 }
 extern "C" int babe_get_cqt_variant(void) { return babe::g_cqt_variant; }
+extern "C" int babe_set_cqt_pdl(int on) {
+  babe::g_cqt_pdl = on;
+  return BABE_OK;
+}
 extern "C" int babe_set_cqt_band_variant(int v) {
   if (v < 0 || v > 3) return BABE_EBADARG;
   babe::g_band_variant = v;

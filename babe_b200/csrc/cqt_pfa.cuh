@@ -524,7 +524,16 @@ struct Pass2 {
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels: grid (tiles, rows)
+//
+// Programmatic dependent launch: every kernel of a CQT chain lets its successor start as soon as all of its own CTAs
+// are running (griddepcontrol.launch_dependents first thing) and builds its tables before it waits for the
+// predecessor's results (griddepcontrol.wait: returns at once for a plain launch).  The successor's launch latency and
+// prologue overlap the predecessor's last wave.  Nothing is read from or written to a buffer of the chain before
+// the wait.
 // ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <class PL, int S>
 __global__ void __launch_bounds__(THREADS, PL::MINB1) k_pfa1_fwd(const float2* __restrict__ x, float2* __restrict__ Y) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -532,8 +541,10 @@ __global__ void __launch_bounds__(THREADS, PL::MINB1) k_pfa1_fwd(const float2* _
   float2* A = reinterpret_cast<float2*>(smem_raw);
   unsigned short* T1 = P::table(A);
   const int tid = threadIdx.x, tile = blockIdx.x;
+  pdl_launch_dependents();
   P::tables(T1, tid);
   __syncthreads();
+  pdl_wait();
   P::load_natural(x + (size_t)blockIdx.y * PL::NC, A, T1, tile, tid);
   __syncthreads();
   P::forward_to_rows(A, Y + (size_t)blockIdx.y * PL::N1 * PL::P2, tile, tid);
@@ -546,7 +557,9 @@ __global__ void __launch_bounds__(THREADS, PL::MINB1) k_pfa1_inv(const float2* _
   float2* A = reinterpret_cast<float2*>(smem_raw);
   unsigned short* T1 = P::table(A);
   const int tid = threadIdx.x, tile = blockIdx.x;
+  pdl_launch_dependents();
   P::tables(T1, tid);
+  pdl_wait();
   P::inverse_from_rows(Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
   P::store_natural(A, x + (size_t)blockIdx.y * PL::NC, T1, tile, tid);
 }
@@ -571,8 +584,10 @@ __global__ void __launch_bounds__(THREADS, PL::MINB2) k_pfa2_fwd(const P2Args a)
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
   const int tid = threadIdx.x, tile = blockIdx.x;
+  pdl_launch_dependents();
   P::tables(A, a.tw_ls, tid);
   __syncthreads();
+  pdl_wait();
   P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
   __syncthreads();
   P::template stages<false>(A, tile, tid);
@@ -588,8 +603,10 @@ __global__ void __launch_bounds__(THREADS, PL::MINB2) k_pfa2_mid(const P2Args a)
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
   const int tid = threadIdx.x, tile = blockIdx.x;
+  pdl_launch_dependents();
   P::tables(A, a.tw_ls, tid);
   __syncthreads();
+  pdl_wait();
   P::load_rows(a.Y + (size_t)blockIdx.y * PL::N1 * PL::P2, A, tile, tid);
   __syncthreads();
   P::template stages<false>(A, tile, tid);
@@ -606,8 +623,10 @@ __global__ void __launch_bounds__(THREADS, PL::MINB2) k_pfa2_inv(const P2Args a)
   using P = Pass2<PL, S>;
   float2* A = reinterpret_cast<float2*>(smem_raw);
   const int tid = threadIdx.x, tile = blockIdx.x;
+  pdl_launch_dependents();
   P::tables(A, a.tw_ls, tid);
   __syncthreads();
+  pdl_wait();
   GatherTab g{GATHER ? a.BS + (size_t)blockIdx.y * a.sum_lg : nullptr, a.src};
   P::template pre_from_x<GATHER>(A, GATHER ? nullptr : a.X + (size_t)blockIdx.y * a.xpitch, g, a.tw_ls, a.scale,
                                  tile, tid);

@@ -124,6 +124,9 @@ if __name__ == "__main__":
 
 def time_cqt():
     from cqt_nsgt_pytorch import CQT_nsgt
+    for a in sys.argv:
+        if a.startswith("pdl="):
+            lib().babe_set_cqt_pdl(int(a[4:]))
     SRc, L = 22050, 184184
     cq = CQT_nsgt(7, 64, mode="oct", window=("kaiser", 1), fs=SRc, audio_len=L, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
