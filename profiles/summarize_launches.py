@@ -26,7 +26,7 @@ for r in rd:
     tot[short][0] += 1
     tot[short][1] += v_us
 total = sum(v[1] for v in tot.values())
-ours = {k: v for k, v in tot.items() if k.startswith("k_")}
+ours = {k: v for k, v in tot.items() if k.startswith(("k_", "pfa::k_"))}
 ours_t = sum(v[1] for v in ours.values())
 print(f"# launch list summary: {path}\n")
 print(f"total kernel time {total/1e3:.2f} ms over {sum(v[0] for v in tot.values())} launches; "
@@ -35,6 +35,6 @@ print("## babe_b200 kernels\n\n| kernel | launches | total us | mean us | share 
 for k, v in sorted(ours.items(), key=lambda kv: -kv[1][1]):
     print(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1]/v[0]:.2f} | {100*v[1]/total:.3f} % |")
 print("\n## top 15 other kernels (PyTorch / cuDNN: the out-of-scope denoiser body)\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
-other = sorted(((k, v) for k, v in tot.items() if not k.startswith("k_")), key=lambda kv: -kv[1][1])[:15]
+other = sorted(((k, v) for k, v in tot.items() if not k.startswith(("k_", "pfa::k_"))), key=lambda kv: -kv[1][1])[:15]
 for k, v in other:
     print(f"| `{k[:90]}` | {v[0]} | {v[1]/1e3:.2f} | {100*v[1]/total:.2f} % |")
