@@ -693,11 +693,14 @@ __device__ __forceinline__ void band_segment(const BandArgs& a, int o, int tile,
 template <bool SYNTH, bool V, bool TMA>
 __device__ __forceinline__ void band_tile(const BandArgs& a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  pfa::pdl_launch_dependents();
+  // The successor of a band kernel is triggered when a CTA is DONE, not when it starts: the grid is one wave of
+  // 128-register CTAs, and successors started at once sit on the SMs next to the running tiles for the whole kernel
+  // (synthesis 0.155 -> 0.178 ms at B = 64 with the early trigger).
   const int o = find_octave(a, blockIdx.x);
   const int row0 = blockIdx.y * a.rows_per_cta, row_end = min(a.B, row0 + a.rows_per_cta);
   if (!V) pfa::pdl_wait();                                  // the packed tiles wait behind their own preamble
   band_segment<SYNTH, V, TMA>(a, o, blockIdx.x - a.tile0[o], row0, row_end, smem_raw);
+  pfa::pdl_launch_dependents();
   if (SYNTH && blockIdx.x == 0 && threadIdx.x < 2)          // the "no band" entries of the rows (a.sum_lg = pitch)
     for (int row = row0; row < row_end; ++row)
       a.BS[(size_t)row * a.sum_lg + a.sum_lg - 2 + threadIdx.x] = make_float2(0.f, 0.f);
@@ -871,8 +874,8 @@ static bool tiled_ok(const babe_cqt_plan* p) {
 }
 
 // ---- programmatic dependent launch of the kernels of a CQT chain (device side: cqt_pfa.cuh) -------------------------
-static int g_cqt_pdl = 7;      // bit mask, A/B: babe_set_cqt_pdl (1: pass-1 kernels, 2: pass-2 kernels, 4: band kernels,
-                               // 8: the gathering inverse pass 2 behind the synthesis band kernel -- off by default)
+static int g_cqt_pdl = 15;     // bit mask, A/B: babe_set_cqt_pdl (1: pass-1 kernels, 2: pass-2 kernels, 4: band kernels,
+                               // 8: the gathering inverse pass 2 behind the synthesis band kernel)
 template <int KIND, class... KArgs, class... Args>
 static void launch_chain(void (*kern)(KArgs...), dim3 grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
@@ -940,8 +943,8 @@ struct PfaRun {
     if (BS != nullptr) {
       a.BS = BS; a.src = reinterpret_cast<const int4*>(p->bin_src); a.sum_lg = bs_pitch(p);
       cudaFuncSetAttribute(pfa::k_pfa2_inv<PL, PFA_S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);
-      // behind the band kernel (128 registers, one wave) an early start of this kernel measured SLOWER (synthesis
-      // 0.155 -> 0.178 ms at B = 64, 0.038 -> 0.044 ms at B = 8): plain stream order for this one edge
+      // its own mask bit: started at the BEGINNING of the band kernel (128 registers, one wave) it measured slower
+      // (synthesis 0.155 -> 0.178 ms at B = 64); the band kernels therefore trigger their successor when a CTA is done
       launch_chain<8>(pfa::k_pfa2_inv<PL, PFA_S, true>, dim3(P2::TILES, B), pfa::THREADS, P2::SMEM, st, a);
     } else {
       cudaFuncSetAttribute(pfa::k_pfa2_inv<PL, PFA_S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2::SMEM);

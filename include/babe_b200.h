@@ -91,7 +91,7 @@ int babe_set_cqt_band_variant(int variant);
 /* Programmatic dependent launch of the kernels of a CQT call: each kernel lets its successor start while its own last
  * wave runs and waits (griddepcontrol.wait) only before it touches the chain's buffers.  Bit mask of the kernels
  * launched that way: 1 pass-1 kernels, 2 pass-2 kernels, 4 band kernels, 8 the gathering inverse pass 2 behind the
- * synthesis band kernel (measured slower, off); default 7, 0 = plain stream-ordered launches (A/B). */
+ * synthesis band kernel; default 15, 0 = plain stream-ordered launches (A/B). */
 int babe_set_cqt_pdl(int mask);
 
 /* ---- a3/a12: fused STFT -> H -> iSTFT ---------------------------------- */
