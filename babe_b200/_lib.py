@@ -57,6 +57,7 @@ SIGNATURES = {
     "babe_get_cqt_variant": (c_int, []),
     "babe_set_cqt_band_variant": (c_int, [c_int]),
     "babe_set_cqt_pdl": (c_int, [c_int]),
+    "babe_set_fit_variant": (c_int, [c_int]),
     "babe_stft_tables_host": (c_int, [c_int, c_void_p, c_void_p]),
     "babe_design_filter": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                    c_void_p, c_void_p, c_void_p]),

@@ -181,6 +181,10 @@ typedef struct {
   int max_iter;            /* optimization.max_iter                    */
   int clamp_fc, clamp_A, only_negative_A;
 } babe_fit_config;
+/* Which kernel runs the loop: 0 (default) k_fit_params3, a cluster of 4 CTAs (each evaluates a quarter of the bins,
+ * sums gathered through distributed shared memory, one serial warp); 1 k_fit_params2 (one CTA); -1 round 1's
+ * k_fit_params.  babe_set_fused_variant(-1 / 0) sets it too. */
+int babe_set_fit_variant(int variant);
 int babe_fit_params(const double* abc, const float* w, const float* freqs, int F,
                     float* params, int K, const babe_fit_config* cfg_host,
                     int* iters_out, void* stream);

@@ -160,15 +160,15 @@ def time_fit():
                   (7, [[200.0, 225, 250, 275, 300, 325, 350], [-15.0, -20, -25, -30, -40, -50, -55]])):
         p0 = torch.tensor(p0, device=dev)
         res = {}
-        for v in (-1, 0):
-            lib().babe_set_fused_variant(v)
+        for v in (-1, 1, 0):
+            lib().babe_set_fit_variant(v)
             med, best = timeit(lambda: fit(x8, y8, p0.clone(), abc=abc), iters=20)
             p, its = fit(x8, y8, p0.clone(), abc=abc, return_iters=True)
             res[v] = p.clone()
             print(json.dumps({"op": "fit_params", "K": K, "variant": v, "ms": round(med, 4), "best_ms": round(best, 4),
                               "iters": int(its)}))
-        print("  max rel diff new vs round-1:", rel(res[0], res[-1]))
-    lib().babe_set_fused_variant(0)
+        print("  max rel diff one-CTA kernel vs round-1:", rel(res[1], res[-1]), " cluster kernel vs round-1:", rel(res[0], res[-1]))
+    lib().babe_set_fit_variant(0)
 
 
 if __name__ == "__main__" and "cqt" in sys.argv[1:]:

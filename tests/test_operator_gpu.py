@@ -215,6 +215,36 @@ def test_fit_params_vs_oracle(golden):
     assert rel_l2(p7.cpu(), g["fit7_p"]) < 3e-2
 
 
+def test_fit_kernels_agree_bitwise(golden):
+    """The three generations of the fit loop -- round 1's k_fit_params (-1), the one-CTA k_fit_params2 (1) and the default
+    4-CTA cluster kernel k_fit_params3 (0: bins split over the CTAs, sums through distributed shared memory) -- evaluate
+    the same fp32 / fp64 expressions; only the association of the fp64 sums over bins differs.  Their 100-iteration
+    trajectories agree to the last bit on the goldens' inputs (K = 5, K = 7, NFFT 1024) and on a 4096-point case."""
+    from babe_b200 import ops, sampler
+    from babe_b200._lib import lib
+    g = golden("fit_sampler.npz")
+    nfft, sr = int(g["nfft"]), int(g["sr"])
+    xden, y = cuda(g["fit_xden"]), cuda(g["y"])
+    cases = [(nfft, xden, y, cuda(g["fit_p0"])), (nfft, xden, y, cuda(g["fit7_p0"]))]
+    gen = torch.Generator().manual_seed(5)
+    x4 = (torch.randn(2, 60000, generator=gen) * 0.063).cuda()
+    f4 = torch.fft.rfftfreq(4096, d=1 / 22050).cuda()
+    y4 = ops.apply_filter(x4, 4096, freqs=f4, fc=torch.tensor([1500.0]).cuda(), A=torch.tensor([-25.0]).cuda())
+    cases.append((4096, x4, y4, torch.tensor([[280.0, 285, 290, 295, 300], [-15.0, -17, -20, -25, -30]]).cuda()))
+    try:
+        for n, xd, yy, p0 in cases:
+            out = {}
+            for v in (-1, 1, 0):
+                assert lib().babe_set_fit_variant(v) == 0
+                fit = sampler.FilterFit(nfft=n, sample_rate=22050 if n == 4096 else sr, max_iter=100, device="cuda")
+                p, its = fit(xd, yy, p0.clone(), return_iters=True)
+                out[v] = (p.cpu(), int(its))
+            assert out[0][1] == out[1][1] == out[-1][1]
+            assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[1][0], out[-1][0])
+    finally:
+        lib().babe_set_fit_variant(0)
+
+
 # --------------------------------------------------------------------------- full-size properties
 @pytest.mark.parametrize("B,T,nfft", [(8, 184184, 4096), (2, 485100, 4096), (64, 184184, 4096), (3, 132300, 1024)])
 def test_full_size_properties(bu, sf, B, T, nfft):
