@@ -603,6 +603,7 @@ __global__ void __cluster_dims__(FIT3_NC, 1, 1) __launch_bounds__(FIT_THREADS, 1
   const bool bp = warp == 0 && lane < K;
   float fc = 0.f, A = 0.f, fc_prev = 0.f, A_prev = 0.f;
   if (bp) { fc = a.params[lane]; A = a.params[K + lane]; }
+  const float f0 = sf[0];
   const float df = F > 1 ? (sf[F - 1] - sf[0]) / (float)(F - 1) : 1.0f;
   const float inv_df = 1.0f / df;
   double c_total = 0.0;
@@ -614,12 +615,23 @@ __global__ void __cluster_dims__(FIT3_NC, 1, 1) __launch_bounds__(FIT_THREADS, 1
     float fkf = 0.f, lgc = 0.f, anchor = 1.0f;
     if (lane < K) {
       if (fc == fc) {                                           // NaN -> F, like first_bin_ge
-        int k = (int)fminf(fmaxf((fc - sf[0]) * inv_df, 0.f), (float)F);
-        while (k > 0 && sf[k - 1] >= fc) --k;
-        while (k < F && sf[k] < fc) ++k;
+        int k = (int)fminf(fmaxf((fc - f0) * inv_df, 0.f), (float)F);
+        // the closed-form guess is within one bin of the answer: its neighbours are loaded together, the loops of the
+        // dependent look-ups only run when that is not enough
+        const float sm1 = sf[max(k - 1, 0)], s0 = sf[min(k, F - 1)], sp1 = sf[min(k + 1, F - 1)];
+        if (k > 0 && sm1 >= fc) {
+          --k;
+          while (k > 0 && sf[k - 1] >= fc) --k;
+          fkf = sf[k];
+        } else if (k < F && s0 < fc) {
+          ++k;
+          if (k < F && sp1 < fc) { ++k; while (k < F && sf[k] < fc) ++k; fkf = k < F ? sf[k] : 0.f; }
+          else fkf = k < F ? sp1 : 0.f;
+        } else {
+          fkf = k < F ? s0 : 0.f;
+        }
         kf = k;
       }
-      fkf = kf < F ? sf[kf] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < K; ++i) {                                // parent = last earlier breakpoint at or below
@@ -786,21 +798,38 @@ __global__ void __cluster_dims__(FIT3_NC, 1, 1) __launch_bounds__(FIT_THREADS, 1
         fc = __fsub_rn(fc, __fmul_rn(a.cfg.mu_fc, (float)(gfc * inv_norm)));       // fp32 step (:569)
         A = __fsub_rn(A, __fmul_rn(a.cfg.mu_A, (float)(gA * inv_norm)));
       }
-      // sequential clamps (:576-583) as shuffle scans: lane k needs lane k-1's CLAMPED value
-      if (a.cfg.clamp_fc) {
-        if (lane == 0) fc = fminf(fmaxf(fc, a.cfg.fcmin), a.cfg.fcmax);
-#pragma unroll
-        for (int k = 1; k < K; ++k) {
-          const float pv = __shfl_sync(0xffffffffu, fc, k - 1);
-          if (lane == k) fc = fminf(fmaxf(fc, __fadd_rn(pv, 1.0f)), a.cfg.fcmax);
+      // sequential clamps (:576-583) as shuffle scans: lane k needs lane k-1's CLAMPED value; the fc and A scans are
+      // independent chains and run interleaved when both are on
+      if (a.cfg.clamp_fc && a.cfg.clamp_A) {
+        if (lane == 0) {
+          fc = fminf(fmaxf(fc, a.cfg.fcmin), a.cfg.fcmax);
+          A = fminf(fmaxf(A, a.cfg.Amin), a.cfg.only_negative_A ? -1.0f : a.cfg.Amax);
         }
-      }
-      if (a.cfg.clamp_A) {
-        if (lane == 0) A = fminf(fmaxf(A, a.cfg.Amin), a.cfg.only_negative_A ? -1.0f : a.cfg.Amax);
 #pragma unroll
         for (int k = 1; k < K; ++k) {
-          const float pv = __shfl_sync(0xffffffffu, A, k - 1);
-          if (lane == k) A = fminf(fmaxf(A, a.cfg.Amin), a.cfg.only_negative_A ? pv : a.cfg.Amax);
+          const float pf = __shfl_sync(0xffffffffu, fc, k - 1);
+          const float pa = __shfl_sync(0xffffffffu, A, k - 1);
+          if (lane == k) {
+            fc = fminf(fmaxf(fc, __fadd_rn(pf, 1.0f)), a.cfg.fcmax);
+            A = fminf(fmaxf(A, a.cfg.Amin), a.cfg.only_negative_A ? pa : a.cfg.Amax);
+          }
+        }
+      } else {
+        if (a.cfg.clamp_fc) {
+          if (lane == 0) fc = fminf(fmaxf(fc, a.cfg.fcmin), a.cfg.fcmax);
+#pragma unroll
+          for (int k = 1; k < K; ++k) {
+            const float pv = __shfl_sync(0xffffffffu, fc, k - 1);
+            if (lane == k) fc = fminf(fmaxf(fc, __fadd_rn(pv, 1.0f)), a.cfg.fcmax);
+          }
+        }
+        if (a.cfg.clamp_A) {
+          if (lane == 0) A = fminf(fmaxf(A, a.cfg.Amin), a.cfg.only_negative_A ? -1.0f : a.cfg.Amax);
+#pragma unroll
+          for (int k = 1; k < K; ++k) {
+            const float pv = __shfl_sync(0xffffffffu, A, k - 1);
+            if (lane == k) A = fminf(fmaxf(A, a.cfg.Amin), a.cfg.only_negative_A ? pv : a.cfg.Amax);
+          }
         }
       }
       // stopping test (:586-588): mean |delta| of fc and of A, summed in breakpoint order like fit_converged
