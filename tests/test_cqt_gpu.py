@@ -191,3 +191,35 @@ def test_other_band_kernels_vs_oracle(CQT, band_variant, numocts, binsoct, fs, L
         assert rel_l2(cq.bwd_planar(cp).cpu(), ref.bwd(cr)) < TOL
     finally:
         lib().babe_set_cqt_band_variant(1)
+
+
+def test_programmatic_launch_is_bitwise_neutral(CQT):
+    """`babe_set_cqt_pdl`: the kernels of a CQT call start behind their predecessor's last wave (programmatic dependent
+    launch) and wait (`griddepcontrol.wait`) before they touch the chain's buffers.  Back-to-back calls that re-use the
+    plan's workspace (the case an early start could corrupt) give bit-identical results with and without it."""
+    from babe_b200._lib import lib
+    cq = CQT(7, 64, mode="oct", window=("kaiser", 1), fs=22050, audio_len=184184, device="cuda")
+    g = torch.Generator().manual_seed(11)
+    xs = [(torch.randn(3, 184184, generator=g) * 0.063).cuda() for _ in range(3)]
+
+    def run():
+        outs = []
+        for _ in range(2):                       # same workspace, different inputs, no host synchronisation in between
+            for x in xs:
+                c = cq.fwd(x.unsqueeze(1))
+                outs.append(cq.bwd(c))
+                outs.append(cq.apply_hpf_DC(x))
+                outs.extend(c)
+        torch.cuda.synchronize()
+        return [o.clone() for o in outs]
+
+    try:
+        assert lib().babe_set_cqt_pdl(0) == 0
+        ref = run()
+        assert lib().babe_set_cqt_pdl(15) == 0
+        got = run()
+    finally:
+        lib().babe_set_cqt_pdl(15)
+    assert len(ref) == len(got)
+    for a, b in zip(ref, got):
+        assert torch.equal(torch.view_as_real(a) if a.is_complex() else a, torch.view_as_real(b) if b.is_complex() else b)
