@@ -199,3 +199,27 @@ def time_cqt_lengths():
 
 if __name__ == "__main__" and "cqtlen" in sys.argv[1:]:
     time_cqt_lengths()
+
+
+def sweep_cqt():
+    """CQT operators over the batch size (Ls = 184184, 7 x 64): profiles/r02_cqt_sweep.jsonl."""
+    from cqt_nsgt_pytorch import CQT_nsgt
+    SRc, L = 22050, 184184
+    cq = CQT_nsgt(7, 64, mode="oct", window=("kaiser", 1), fs=SRc, audio_len=L, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256):
+        xc = torch.randn(B, L, device=dev) * 0.063
+        cs = cq.fwd(xc.unsqueeze(1))
+        cp = cq.fwd_planar(xc)
+        cqb = B * (4 * L + 8 * cq.plan.coef_per_row)
+        for name, fn, nb in (("cqt_analysis", lambda: cq.fwd(xc.unsqueeze(1)), cqb), ("cqt_synthesis", lambda: cq.bwd(cs), cqb),
+                             ("cqt_analysis_planar", lambda: cq.fwd_planar(xc), cqb), ("cqt_synthesis_planar", lambda: cq.bwd_planar(cp), cqb),
+                             ("hpf_DC", lambda: cq.apply_hpf_DC(xc), B * 8 * L)):
+            med, best = timeit(fn, flush=flush)
+            print(json.dumps({"B": B, "op": name, "ms": round(med, 4), "best_ms": round(best, 4), "GBps": round(nb / med / 1e6, 1),
+                              "frac": round(nb / med / 1e6 / PEAK, 4)}))
+        del xc, cs, cp
+
+
+if __name__ == "__main__" and "cqtsweep" in sys.argv[1:]:
+    sweep_cqt()
