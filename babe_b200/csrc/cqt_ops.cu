@@ -969,11 +969,11 @@ struct PfaRun {
   }
 };
 
-// 8-column tiles while 16-column tiles would fill less than four of the 4-5 CTA slots per SM (B <= ~30 rows at
-// Ls = 184184; measured at B = 16: apply_hpf_DC 0.046 -> 0.038 ms, analysis 0.045 -> 0.043 ms)
+// 8-column tiles while 16-column tiles would give fewer than ~2 waves of CTAs (B <= ~60 rows at Ls = 184184;
+// measured: apply_hpf_DC 0.046 -> 0.038 ms at B = 16, 0.063 -> 0.060 ms at B = 32; a wash at B = 64)
 #define BABE_PFA_DISPATCH_PLAN(PL, call)                                                          \
   do {                                                                                            \
-    const bool small = (long long)B * ((PL::N2 + 15) / 16) < 4LL * sm_count();                    \
+    const bool small = (long long)B * ((PL::N2 + 15) / 16) < 8LL * sm_count();                    \
     return small ? PfaRun<PL, 8>::call : PfaRun<PL, 16>::call;                                    \
   } while (0)
 #define BABE_PFA_DISPATCH(call)                                                                   \
