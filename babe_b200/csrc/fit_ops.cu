@@ -599,6 +599,7 @@ __global__ void __cluster_dims__(FIT3_NC, 1, 1) __launch_bounds__(FIT_THREADS, 1
   if (lane == 0) red[warp][16] = ct;
   if (tid == 0) stop_flag = 0;
   __syncthreads();
+  cluster.sync();          // a peer's shared memory may only be addressed once the peer is known to have started
   // ---- breakpoint state in the registers of warp 0, lanes 0..K-1 --------------------------------------------
   const bool bp = warp == 0 && lane < K;
   float fc = 0.f, A = 0.f, fc_prev = 0.f, A_prev = 0.f;
