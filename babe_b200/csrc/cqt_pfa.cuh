@@ -264,6 +264,10 @@ struct Pass1 {
         }
       } else {
         if (live) dft_io<R, INV>(a, CI * S, Yout + (size_t)e0 * PL::P2 + r, CI * PL::P2);
+        if (PL::P2 > PL::N2 && r == PL::N2 - 1) {     // the pad element of the rows: read (and ignored) as half of a 16-byte load
+#pragma unroll
+          for (int d = 0; d < R; ++d) Yout[(size_t)(e0 + d * CI) * PL::P2 + PL::N2] = make_float2(0.f, 0.f);
+        }
       }
     }
   }
