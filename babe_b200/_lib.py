@@ -94,6 +94,9 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "babe_spec_mag_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p]),
+    "babe_spec_dist_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "babe_spec_dist_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_void_p, c_void_p, c_void_p]),
     "babe_fit_params": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                 POINTER(FitConfig), c_void_p, c_void_p]),
     "babe_cqt_workspace": (c_size_t, [POINTER(CqtPlan), c_int]),

@@ -184,6 +184,37 @@ def design_filter_G(fc, A, G, f):
     return _DesignFilter.apply(_as_param(fc, f), _as_param(A, f), f, _as_param(G, f))
 
 
+
+class _SpecDist(torch.autograd.Function):
+    """The STFT-guidance distances on spectrograms: mode 0 = || w X - w Xref ||_2 (utils/blind_bwe_utils.py:148-197),
+    mode 1 = || w|X| - w|Xref| ||_2 and mode 2 = its log10(. + 1e-8) form (:198-248).  One reduction kernel forward,
+    one element-wise kernel backward (what the reference's autograd chain computes), no weighted copies in HBM."""
+
+    @staticmethod
+    def forward(ctx, X, Xref, w, mode):
+        if mode == 1:
+            ss = ops.spec_mag_stats(X, Xref, H=None, w=w)[3]
+        else:
+            ss = ops.spec_dist_stats(X, Xref, w=w, mode=mode)
+        norm64 = torch.sqrt(ss.sum())
+        ctx.mode, ctx.has_w = mode, w is not None
+        ctx.save_for_backward(X, Xref, w if w is not None else torch.empty(0, device=X.device), norm64)
+        return norm64.to(torch.float32)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        X, Xref, w, norm64 = ctx.saved_tensors
+        w = w if ctx.has_w else None
+        coef = (g.double() / norm64).to(torch.float32)
+        want = dict(want_X=ctx.needs_input_grad[0], want_Xref=ctx.needs_input_grad[1])
+        if ctx.mode == 1:
+            gX, gR = ops.spec_mag_grad(X, Xref, None, w, coef, **want)
+        else:
+            gX, gR = ops.spec_dist_grad(X, Xref, w, coef, mode=ctx.mode, **want)
+        return gX, gR, None, None
+
+
 def freq_weight_vector(freq_weight, F, device):
     """Per-bin multiplier for each ``freq_weight`` string
     (utils/blind_bwe_utils.py:260-293); unknown strings apply no weighting,
@@ -221,26 +252,15 @@ def apply_norm_STFT_fweighted(y, den_rec, freq_weight="linear", NFFT=1024):
     X = apply_stft(den_rec, NFFT)
     Xref = apply_stft(y, NFFT)
     w = freq_weight_vector(freq_weight, X.shape[1], X.device)
-    if w is not None:
-        X = X * w[None, :, None, None]
-        Xref = Xref * w[None, :, None, None]
-    return torch.linalg.norm(X.reshape(-1) - Xref.reshape(-1), ord=2)
+    return _SpecDist.apply(X, Xref, w, 0)
 
 
 def apply_norm_STFTmag_fweighted(y, den_rec, freq_weight="linear", NFFT=1024, logmag=False):
     """utils/blind_bwe_utils.py:198-248."""
     X = apply_stft(den_rec, NFFT)
     Xref = apply_stft(y, NFFT)
-    X = torch.sqrt(X[..., 0] ** 2 + X[..., 1] ** 2)
-    Xref = torch.sqrt(Xref[..., 0] ** 2 + Xref[..., 1] ** 2)
     w = freq_weight_vector(freq_weight, X.shape[1], X.device)
-    if w is not None:
-        X = X * w[None, :, None]
-        Xref = Xref * w[None, :, None]
-    if logmag == True:  # noqa: E712  (the reference compares with == True)
-        return torch.linalg.norm(torch.log10(X.reshape(-1) + 1e-8)
-                                 - torch.log10(Xref.reshape(-1) + 1e-8), ord=2)
-    return torch.linalg.norm(X.reshape(-1) - Xref.reshape(-1), ord=2)
+    return _SpecDist.apply(X, Xref, w, 2 if logmag == True else 1)  # noqa: E712  (the reference compares with == True)
 
 
 def apply_filter_and_norm_STFTmag_fweighted(X, Xref, H, freq_weight="linear"):

@@ -909,6 +909,70 @@ __global__ void __launch_bounds__(256) k_spec_mag_grad(const float2* X, const fl
   }
 }
 
+// ---------------------------------------------------------------------------
+// spectrogram distances of the STFT-guidance branches (utils/blind_bwe_utils.py:148-197 complex, :198-248 log-magnitude;
+// the plain magnitude distance is k_spec_mag_stats / k_spec_mag_grad with H = 1): one pass over both spectrograms
+// instead of the reference's multiply / subtract / norm chain.  MODE 0: s_k = sum |w X - w Xref|^2,
+// MODE 2: s_k = sum (log10(w|X| + 1e-8) - log10(w|Xref| + 1e-8))^2; fp32 in the reference's operation order,
+// accumulated in double.
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k_spec_dist_stats(const float2* X, const float2* Xref, const float* w, int B,
+                                                         int F, int frames, double* out) {
+  const int k = blockIdx.x;
+  const float wk = w ? w[k] : 1.0f;
+  double ss = 0;
+  const long long n = (long long)B * frames;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = (int)(i / frames), m = (int)(i % frames);
+    const size_t off = ((size_t)b * F + k) * frames + m;
+    const float2 x = X[off], y = Xref[off];
+    if (MODE == 0) {
+      const float dr = __fsub_rn(__fmul_rn(x.x, wk), __fmul_rn(y.x, wk));
+      const float di = __fsub_rn(__fmul_rn(x.y, wk), __fmul_rn(y.y, wk));
+      ss += (double)dr * dr + (double)di * di;
+    } else {
+      const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+      const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
+      const float d = __fsub_rn(log10f(__fadd_rn(__fmul_rn(mx, wk), 1e-8f)), log10f(__fadd_rn(__fmul_rn(my, wk), 1e-8f)));
+      ss += (double)d * d;
+    }
+  }
+  __shared__ double red[4];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) out[k] = red[0] + red[1] + red[2] + red[3];
+}
+
+// gradients of those norms wrt the spectrograms (coef = upstream gradient / norm, device scalar):
+// MODE 0: gX = coef w^2 (X - Xref) = -gXref;
+// MODE 2: gX = coef d w X / (|X| (w|X| + 1e-8) ln 10), gXref = -coef d w Xref / (|Xref| (w|Xref| + 1e-8) ln 10).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_spec_dist_grad(const float2* X, const float2* Xref, const float* w,
+                                                        const float* coef, int F, int frames, long long n,
+                                                        float2* gX, float2* gXref) {
+  const float c = coef[0];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)((i / frames) % F);
+    const float wk = w ? w[k] : 1.0f;
+    const float2 x = X[i], y = Xref[i];
+    if (MODE == 0) {
+      const float gr = c * wk * __fsub_rn(__fmul_rn(x.x, wk), __fmul_rn(y.x, wk));
+      const float gi = c * wk * __fsub_rn(__fmul_rn(x.y, wk), __fmul_rn(y.y, wk));
+      if (gX) gX[i] = make_float2(gr, gi);
+      if (gXref) gXref[i] = make_float2(-gr, -gi);
+    } else {
+      const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+      const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
+      const float ax = __fadd_rn(__fmul_rn(mx, wk), 1e-8f), ay = __fadd_rn(__fmul_rn(my, wk), 1e-8f);
+      const float e = c * __fsub_rn(log10f(ax), log10f(ay)) * wk * 0.43429448190325176f;
+      if (gX) { const float s = e / (ax * mx); gX[i] = make_float2(s * x.x, s * x.y); }
+      if (gXref) { const float s = -e / (ay * my); gXref[i] = make_float2(s * y.x, s * y.y); }
+    }
+  }
+}
+
 static int g_fit_variant = 0;     // 0: k_fit_params3 (4-CTA cluster), 1: k_fit_params2 (one CTA), -1: round-1 k_fit_params
                                   // (A/B: babe_set_fit_variant; babe_set_fused_variant(-1 / 0) sets it too)
 void set_fit_variant(int v) { g_fit_variant = v; }
@@ -1011,4 +1075,34 @@ extern "C" int babe_spec_mag_grad(const float* X, const float* Xref, const float
       reinterpret_cast<const float2*>(X), reinterpret_cast<const float2*>(Xref), H, w, coef, F, frames, n,
       reinterpret_cast<float2*>(gX), reinterpret_cast<float2*>(gXref));
   return check_launch("k_spec_mag_grad");
+}
+
+extern "C" int babe_spec_dist_stats(const float* X, const float* Xref, const float* w, int mode, int B, int F,
+                                    int frames, double* out, void* stream) {
+  BABE_REQUIRE(X && Xref && out, BABE_EBADARG, "spec_dist_stats: null pointer");
+  BABE_REQUIRE(B >= 1 && F >= 1 && frames >= 1, BABE_EBADARG, "spec_dist_stats: bad shape");
+  BABE_REQUIRE(mode == 0 || mode == 2, BABE_EBADARG, "spec_dist_stats: mode=%d (0 complex, 2 log-magnitude)", mode);
+  const float2* x = reinterpret_cast<const float2*>(X);
+  const float2* y = reinterpret_cast<const float2*>(Xref);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == 0) k_spec_dist_stats<0><<<F, 128, 0, st>>>(x, y, w, B, F, frames, out);
+  else k_spec_dist_stats<2><<<F, 128, 0, st>>>(x, y, w, B, F, frames, out);
+  return check_launch("k_spec_dist_stats");
+}
+
+extern "C" int babe_spec_dist_grad(const float* X, const float* Xref, const float* w, const float* coef, int mode,
+                                   int B, int F, int frames, float* gX, float* gXref, void* stream) {
+  BABE_REQUIRE(X && Xref && coef && (gX || gXref), BABE_EBADARG, "spec_dist_grad: null pointer");
+  BABE_REQUIRE(B >= 1 && F >= 1 && frames >= 1, BABE_EBADARG, "spec_dist_grad: bad shape");
+  BABE_REQUIRE(mode == 0 || mode == 2, BABE_EBADARG, "spec_dist_grad: mode=%d (0 complex, 2 log-magnitude)", mode);
+  const long long n = (long long)B * F * frames;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+  const float2* x = reinterpret_cast<const float2*>(X);
+  const float2* y = reinterpret_cast<const float2*>(Xref);
+  float2* gx = reinterpret_cast<float2*>(gX);
+  float2* gy = reinterpret_cast<float2*>(gXref);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == 0) k_spec_dist_grad<0><<<grid, 256, 0, st>>>(x, y, w, coef, F, frames, n, gx, gy);
+  else k_spec_dist_grad<2><<<grid, 256, 0, st>>>(x, y, w, coef, F, frames, n, gx, gy);
+  return check_launch("k_spec_dist_grad");
 }

@@ -221,6 +221,36 @@ def spec_mag_grad(X, Xref, H, w, coef, want_X=True, want_Xref=False):
     return gX, gR
 
 
+def spec_dist_stats(X, Xref, w=None, mode=0):
+    """float64[F] per-bin sums of squares of the complex (mode 0) / log-magnitude (mode 2) spectrogram distance."""
+    X = _cuda_f32(X, "X")
+    Xref = _cuda_f32(Xref, "Xref")
+    if X.shape != Xref.shape or X.dim() != 4 or X.shape[-1] != 2:
+        raise ValueError("X and Xref must both be (B, F, frames, 2)")
+    B, F, M, _ = X.shape
+    w = None if w is None else _cuda_f32(w, "w")
+    out = torch.empty(F, dtype=torch.float64, device=X.device)
+    with profiling.op("spec_dist_stats", 1, 2 * X.numel() * 4):
+        check(lib().babe_spec_dist_stats(_p(X), _p(Xref), _p(w), int(mode), B, F, M, _p(out), _stream()),
+              "spec_dist_stats")
+    return out
+
+
+def spec_dist_grad(X, Xref, w, coef, mode=0, want_X=True, want_Xref=False):
+    """Gradients of the mode-0 / mode-2 spectrogram distance wrt the spectrograms; coef: 1-element CUDA tensor."""
+    X = _cuda_f32(X, "X")
+    Xref = _cuda_f32(Xref, "Xref")
+    B, F, M, _ = X.shape
+    w = None if w is None else _cuda_f32(w, "w")
+    coef = _cuda_f32(coef, "coef").reshape(1)
+    gX = torch.empty_like(X) if want_X else None
+    gR = torch.empty_like(Xref) if want_Xref else None
+    with profiling.op("spec_dist_grad", 1, 4 * X.numel() * (2 + int(want_X) + int(want_Xref))):
+        check(lib().babe_spec_dist_grad(_p(X), _p(Xref), _p(w), _p(coef), int(mode), B, F, M, _p(gX), _p(gR),
+                                        _stream()), "spec_dist_grad")
+    return gX, gR
+
+
 def fit_params(abc, w, freqs, params, cfg, return_iters=False):
     """Run the device-resident projected gradient descent IN PLACE on
     params[2,K] (float32, CUDA, contiguous)."""

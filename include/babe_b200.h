@@ -167,6 +167,18 @@ int babe_spec_mag_stats(const float* X, const float* Xref, const float* H, const
 int babe_spec_mag_grad(const float* X, const float* Xref, const float* H, const float* w, const float* coef,
                        int B, int F, int frames, float* gX, float* gXref, void* stream);
 
+/* a9 / a10: the STFT-distance guidance norms apply_norm_STFT_fweighted (utils/blind_bwe_utils.py:148-197, mode 0:
+ * || w X - w Xref ||_2 over re/im) and apply_norm_STFTmag_fweighted(..., logmag=True) (:198-248, mode 2:
+ * || log10(w|X| + 1e-8) - log10(w|Xref| + 1e-8) ||_2) from spectrograms [B,F,frames,2]; out is double[F], the per-bin
+ * sums of squares (norm = sqrt of their sum).  The plain magnitude distance (:198-248, logmag=False) is
+ * babe_spec_mag_stats with H = NULL.  w may be NULL (= 1). */
+int babe_spec_dist_stats(const float* X, const float* Xref, const float* w, int mode, int B, int F, int frames,
+                         double* out, void* stream);
+/* Gradients of those norms wrt the spectrograms; coef is a 1-element DEVICE array (upstream gradient / norm);
+ * either output may be NULL. */
+int babe_spec_dist_grad(const float* X, const float* Xref, const float* w, const float* coef, int mode, int B, int F,
+                        int frames, float* gX, float* gXref, void* stream);
+
 /* ---- a7: device-resident filter fit ------------------------------------ */
 /* Replaces the Python loop of BlindSampler.fit_params
  * (testing/blind_bwe_sampler.py:562-590): projected gradient descent on

@@ -31,3 +31,14 @@ def golden():
     def load(name):
         return dict(np.load(os.path.join(GOLDEN, name)))
     return load
+
+
+@pytest.fixture(autouse=True)
+def _fp32_parity(request):
+    """Every GPU parity test compares with fp32 results of the reference / oracle on the host: keep cuDNN and cuBLAS
+    out of TF32 for all of them, so that no test depends on an earlier module having switched it off."""
+    if request.node.get_closest_marker("gpu") is not None:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    yield
