@@ -858,33 +858,50 @@ __global__ void __cluster_dims__(FIT3_NC, 1, 1) __launch_bounds__(FIT_THREADS, 1
 // ---------------------------------------------------------------------------
 // spectrogram-domain magnitude statistics: one CTA per frequency bin
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_spec_mag_stats(const float2* X, const float2* Xref,
-                                                        const float* H, const float* w, int B,
-                                                        int F, int frames, double* out) {
+// work item = one 32-frame segment of one (row b, bin k) line of the spectrogram: a warp reads 256 contiguous bytes per
+// load and no thread divides 64-bit indices
+constexpr int SPEC_THREADS = 256;
+constexpr int SPEC_UNROLL = 4;
+__global__ void __launch_bounds__(SPEC_THREADS) k_spec_mag_stats(const float2* X, const float2* Xref,
+                                                                 const float* H, const float* w, int B,
+                                                                 int F, int frames, double* out) {
   const int k = blockIdx.x;
   const float h = H ? H[k] : 1.0f;
   const float wk = w ? w[k] : 1.0f;
   double sa = 0, sb = 0, sc = 0, ss = 0;
-  const long long n = (long long)B * frames;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int b = (int)(i / frames), m = (int)(i % frames);
-    const size_t off = ((size_t)b * F + k) * frames + m;
-    const float2 x = X[off], y = Xref[off];
-    // mirror the reference's fp32 order: sqrt(re^2+im^2), *H, *w, difference
-    const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
-    const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
-    const float d = __fsub_rn(__fmul_rn(__fmul_rn(mx, h), wk), __fmul_rn(my, wk));
-    sa += (double)mx * mx; sb += (double)mx * my; sc += (double)my * my;
-    ss += (double)d * d;
-  }
-  __shared__ double red[4][4];
-  sa = warp_sum(sa); sb = warp_sum(sb); sc = warp_sum(sc); ss = warp_sum(ss);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nseg = (frames + 31) >> 5, items = B * nseg;
+  for (int it0 = warp; it0 < items; it0 += SPEC_UNROLL * (SPEC_THREADS / 32)) {
+    float2 x[SPEC_UNROLL], y[SPEC_UNROLL];
+    bool ok[SPEC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SPEC_UNROLL; ++u) {              // all loads of the group in flight before the arithmetic
+      const int it = it0 + u * (SPEC_THREADS / 32);
+      const int b = it / nseg, m = (it - b * nseg) * 32 + lane;
+      ok[u] = it < items && m < frames;
+      if (ok[u]) {
+        const size_t off = ((size_t)b * F + k) * frames + m;
+        x[u] = X[off]; y[u] = Xref[off];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SPEC_UNROLL; ++u) {
+      if (!ok[u]) continue;
+      // mirror the reference's fp32 order: sqrt(re^2+im^2), *H, *w, difference
+      const float mx = sqrtf(__fadd_rn(__fmul_rn(x[u].x, x[u].x), __fmul_rn(x[u].y, x[u].y)));
+      const float my = sqrtf(__fadd_rn(__fmul_rn(y[u].x, y[u].x), __fmul_rn(y[u].y, y[u].y)));
+      const float d = __fsub_rn(__fmul_rn(__fmul_rn(mx, h), wk), __fmul_rn(my, wk));
+      sa += (double)mx * mx; sb += (double)mx * my; sc += (double)my * my;
+      ss += (double)d * d;
+    }
+  }
+  __shared__ double red[SPEC_THREADS / 32][4];
+  sa = warp_sum(sa); sb = warp_sum(sb); sc = warp_sum(sc); ss = warp_sum(ss);
   if (lane == 0) { red[warp][0] = sa; red[warp][1] = sb; red[warp][2] = sc; red[warp][3] = ss; }
   __syncthreads();
   if (threadIdx.x < 4) {
     double s = 0;
-    for (int wv = 0; wv < 4; ++wv) s += red[wv][threadIdx.x];
+    for (int wv = 0; wv < SPEC_THREADS / 32; ++wv) s += red[wv][threadIdx.x];
     out[(size_t)threadIdx.x * F + k] = s;
   }
 }
@@ -892,20 +909,26 @@ __global__ void __launch_bounds__(128) k_spec_mag_stats(const float2* X, const f
 // gradient of  norm = || w (H |X| - |Xref|) ||_2  wrt the spectrograms (utils/blind_bwe_utils.py:250-296 under
 // autograd):  dnorm/dX = coef w^2 (H|X| - |Xref|) H X/|X|,   dnorm/dXref = -coef w^2 (H|X| - |Xref|) Xref/|Xref|,
 // coef = upstream gradient / norm (device scalar).  |X| = 0 gives 0/0 = NaN exactly like the reference's sqrt'.
-__global__ void __launch_bounds__(256) k_spec_mag_grad(const float2* X, const float2* Xref, const float* H,
-                                                       const float* w, const float* coef, int F, int frames,
-                                                       long long n, float2* gX, float2* gXref) {
+__global__ void __launch_bounds__(SPEC_THREADS) k_spec_mag_grad(const float2* X, const float2* Xref, const float* H,
+                                                                const float* w, const float* coef, int F, int frames,
+                                                                int rows, float2* gX, float2* gXref) {
   const float c = coef[0];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)((i / frames) % F);
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (SPEC_THREADS / 32);
+  for (int r = blockIdx.x * (SPEC_THREADS / 32) + (threadIdx.x >> 5); r < rows; r += nwarps) {   // r = b F + k
+    const int k = r % F;
     const float h = H ? H[k] : 1.0f, wk = w ? w[k] : 1.0f;
-    const float2 x = X[i], y = Xref[i];
-    const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
-    const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
-    const float d = __fsub_rn(__fmul_rn(__fmul_rn(mx, h), wk), __fmul_rn(my, wk));
-    const float e = c * d * wk;
-    if (gX) { const float s = e * h / mx; gX[i] = make_float2(s * x.x, s * x.y); }
-    if (gXref) { const float s = -e / my; gXref[i] = make_float2(s * y.x, s * y.y); }
+    const size_t base = (size_t)r * frames;
+    for (int m = lane; m < frames; m += 32) {
+      const size_t i = base + m;
+      const float2 x = X[i], y = Xref[i];
+      const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+      const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
+      const float d = __fsub_rn(__fmul_rn(__fmul_rn(mx, h), wk), __fmul_rn(my, wk));
+      const float e = c * d * wk;
+      if (gX) { const float s = e * h / mx; gX[i] = make_float2(s * x.x, s * x.y); }
+      if (gXref) { const float s = -e / my; gXref[i] = make_float2(s * y.x, s * y.y); }
+    }
   }
 }
 
@@ -917,58 +940,84 @@ __global__ void __launch_bounds__(256) k_spec_mag_grad(const float2* X, const fl
 // accumulated in double.
 // ---------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(128) k_spec_dist_stats(const float2* X, const float2* Xref, const float* w, int B,
-                                                         int F, int frames, double* out) {
+__global__ void __launch_bounds__(SPEC_THREADS) k_spec_dist_stats(const float2* X, const float2* Xref, const float* w,
+                                                                  int B, int F, int frames, double* out) {
   const int k = blockIdx.x;
   const float wk = w ? w[k] : 1.0f;
   double ss = 0;
-  const long long n = (long long)B * frames;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int b = (int)(i / frames), m = (int)(i % frames);
-    const size_t off = ((size_t)b * F + k) * frames + m;
-    const float2 x = X[off], y = Xref[off];
-    if (MODE == 0) {
-      const float dr = __fsub_rn(__fmul_rn(x.x, wk), __fmul_rn(y.x, wk));
-      const float di = __fsub_rn(__fmul_rn(x.y, wk), __fmul_rn(y.y, wk));
-      ss += (double)dr * dr + (double)di * di;
-    } else {
-      const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
-      const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
-      const float d = __fsub_rn(log10f(__fadd_rn(__fmul_rn(mx, wk), 1e-8f)), log10f(__fadd_rn(__fmul_rn(my, wk), 1e-8f)));
-      ss += (double)d * d;
+  float part = 0.0f;                       // fp32 partial over one group of work items, folded into the double sum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nseg = (frames + 31) >> 5, items = B * nseg;
+  for (int it0 = warp; it0 < items; it0 += SPEC_UNROLL * (SPEC_THREADS / 32)) {
+    float2 x[SPEC_UNROLL], y[SPEC_UNROLL];
+    bool ok[SPEC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SPEC_UNROLL; ++u) {              // all loads of the group in flight before the arithmetic
+      const int it = it0 + u * (SPEC_THREADS / 32);
+      const int b = it / nseg, m = (it - b * nseg) * 32 + lane;
+      ok[u] = it < items && m < frames;
+      if (ok[u]) {
+        const size_t off = ((size_t)b * F + k) * frames + m;
+        x[u] = X[off]; y[u] = Xref[off];
+      }
     }
+#pragma unroll
+    for (int u = 0; u < SPEC_UNROLL; ++u) {
+      if (!ok[u]) continue;
+      if (MODE == 0) {
+        const float dr = __fsub_rn(__fmul_rn(x[u].x, wk), __fmul_rn(y[u].x, wk));
+        const float di = __fsub_rn(__fmul_rn(x[u].y, wk), __fmul_rn(y[u].y, wk));
+        part = fmaf(dr, dr, fmaf(di, di, part));
+      } else {
+        const float mx = sqrtf(__fadd_rn(__fmul_rn(x[u].x, x[u].x), __fmul_rn(x[u].y, x[u].y)));
+        const float my = sqrtf(__fadd_rn(__fmul_rn(y[u].x, y[u].x), __fmul_rn(y[u].y, y[u].y)));
+        const float d = __fsub_rn(log10f(__fadd_rn(__fmul_rn(mx, wk), 1e-8f)), log10f(__fadd_rn(__fmul_rn(my, wk), 1e-8f)));
+        part = fmaf(d, d, part);
+      }
+    }
+    ss += (double)part; part = 0.0f;
   }
-  __shared__ double red[4];
+  ss += (double)part;
+  __shared__ double red[SPEC_THREADS / 32];
   ss = warp_sum(ss);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  if (lane == 0) red[warp] = ss;
   __syncthreads();
-  if (threadIdx.x == 0) out[k] = red[0] + red[1] + red[2] + red[3];
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int wv = 0; wv < SPEC_THREADS / 32; ++wv) s += red[wv];
+    out[k] = s;
+  }
 }
 
 // gradients of those norms wrt the spectrograms (coef = upstream gradient / norm, device scalar):
 // MODE 0: gX = coef w^2 (X - Xref) = -gXref;
 // MODE 2: gX = coef d w X / (|X| (w|X| + 1e-8) ln 10), gXref = -coef d w Xref / (|Xref| (w|Xref| + 1e-8) ln 10).
 template <int MODE>
-__global__ void __launch_bounds__(256) k_spec_dist_grad(const float2* X, const float2* Xref, const float* w,
-                                                        const float* coef, int F, int frames, long long n,
-                                                        float2* gX, float2* gXref) {
+__global__ void __launch_bounds__(SPEC_THREADS) k_spec_dist_grad(const float2* X, const float2* Xref, const float* w,
+                                                                 const float* coef, int F, int frames, int rows,
+                                                                 float2* gX, float2* gXref) {
   const float c = coef[0];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)((i / frames) % F);
-    const float wk = w ? w[k] : 1.0f;
-    const float2 x = X[i], y = Xref[i];
-    if (MODE == 0) {
-      const float gr = c * wk * __fsub_rn(__fmul_rn(x.x, wk), __fmul_rn(y.x, wk));
-      const float gi = c * wk * __fsub_rn(__fmul_rn(x.y, wk), __fmul_rn(y.y, wk));
-      if (gX) gX[i] = make_float2(gr, gi);
-      if (gXref) gXref[i] = make_float2(-gr, -gi);
-    } else {
-      const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
-      const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
-      const float ax = __fadd_rn(__fmul_rn(mx, wk), 1e-8f), ay = __fadd_rn(__fmul_rn(my, wk), 1e-8f);
-      const float e = c * __fsub_rn(log10f(ax), log10f(ay)) * wk * 0.43429448190325176f;
-      if (gX) { const float s = e / (ax * mx); gX[i] = make_float2(s * x.x, s * x.y); }
-      if (gXref) { const float s = -e / (ay * my); gXref[i] = make_float2(s * y.x, s * y.y); }
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (SPEC_THREADS / 32);
+  for (int r = blockIdx.x * (SPEC_THREADS / 32) + (threadIdx.x >> 5); r < rows; r += nwarps) {   // r = b F + k
+    const float wk = w ? w[r % F] : 1.0f;
+    const size_t base = (size_t)r * frames;
+    for (int m = lane; m < frames; m += 32) {
+      const size_t i = base + m;
+      const float2 x = X[i], y = Xref[i];
+      if (MODE == 0) {
+        const float gr = c * wk * __fsub_rn(__fmul_rn(x.x, wk), __fmul_rn(y.x, wk));
+        const float gi = c * wk * __fsub_rn(__fmul_rn(x.y, wk), __fmul_rn(y.y, wk));
+        if (gX) gX[i] = make_float2(gr, gi);
+        if (gXref) gXref[i] = make_float2(-gr, -gi);
+      } else {
+        const float mx = sqrtf(__fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y)));
+        const float my = sqrtf(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
+        const float ax = __fadd_rn(__fmul_rn(mx, wk), 1e-8f), ay = __fadd_rn(__fmul_rn(my, wk), 1e-8f);
+        const float e = c * __fsub_rn(log10f(ax), log10f(ay)) * wk * 0.43429448190325176f;
+        if (gX) { const float s = e / (ax * mx); gX[i] = make_float2(s * x.x, s * x.y); }
+        if (gXref) { const float s = -e / (ay * my); gXref[i] = make_float2(s * y.x, s * y.y); }
+      }
     }
   }
 }
@@ -1058,7 +1107,7 @@ extern "C" int babe_spec_mag_stats(const float* X, const float* Xref, const floa
                                    void* stream) {
   BABE_REQUIRE(X && Xref && out, BABE_EBADARG, "spec_mag_stats: null pointer");
   BABE_REQUIRE(B >= 1 && F >= 1 && frames >= 1, BABE_EBADARG, "spec_mag_stats: bad shape");
-  k_spec_mag_stats<<<F, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  k_spec_mag_stats<<<F, SPEC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float2*>(X), reinterpret_cast<const float2*>(Xref), H, w, B, F,
       frames, out);
   return check_launch("k_spec_mag_stats");
@@ -1069,10 +1118,11 @@ extern "C" int babe_spec_mag_grad(const float* X, const float* Xref, const float
                                   void* stream) {
   BABE_REQUIRE(X && Xref && coef && (gX || gXref), BABE_EBADARG, "spec_mag_grad: null pointer");
   BABE_REQUIRE(B >= 1 && F >= 1 && frames >= 1, BABE_EBADARG, "spec_mag_grad: bad shape");
-  const long long n = (long long)B * F * frames;
-  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
-  k_spec_mag_grad<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float2*>(X), reinterpret_cast<const float2*>(Xref), H, w, coef, F, frames, n,
+  BABE_REQUIRE((long long)B * F <= 0x7fffffffLL, BABE_EUNSUPPORTED, "spec_mag_grad: B*F too large");
+  const int rows = B * F;                  // one warp per (row, bin) line of `frames` complex values
+  const int grid = std::min((rows + SPEC_THREADS / 32 - 1) / (SPEC_THREADS / 32), sm_count() * 8);
+  k_spec_mag_grad<<<grid, SPEC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(X), reinterpret_cast<const float2*>(Xref), H, w, coef, F, frames, rows,
       reinterpret_cast<float2*>(gX), reinterpret_cast<float2*>(gXref));
   return check_launch("k_spec_mag_grad");
 }
@@ -1085,8 +1135,8 @@ extern "C" int babe_spec_dist_stats(const float* X, const float* Xref, const flo
   const float2* x = reinterpret_cast<const float2*>(X);
   const float2* y = reinterpret_cast<const float2*>(Xref);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode == 0) k_spec_dist_stats<0><<<F, 128, 0, st>>>(x, y, w, B, F, frames, out);
-  else k_spec_dist_stats<2><<<F, 128, 0, st>>>(x, y, w, B, F, frames, out);
+  if (mode == 0) k_spec_dist_stats<0><<<F, SPEC_THREADS, 0, st>>>(x, y, w, B, F, frames, out);
+  else k_spec_dist_stats<2><<<F, SPEC_THREADS, 0, st>>>(x, y, w, B, F, frames, out);
   return check_launch("k_spec_dist_stats");
 }
 
@@ -1095,14 +1145,15 @@ extern "C" int babe_spec_dist_grad(const float* X, const float* Xref, const floa
   BABE_REQUIRE(X && Xref && coef && (gX || gXref), BABE_EBADARG, "spec_dist_grad: null pointer");
   BABE_REQUIRE(B >= 1 && F >= 1 && frames >= 1, BABE_EBADARG, "spec_dist_grad: bad shape");
   BABE_REQUIRE(mode == 0 || mode == 2, BABE_EBADARG, "spec_dist_grad: mode=%d (0 complex, 2 log-magnitude)", mode);
-  const long long n = (long long)B * F * frames;
-  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+  BABE_REQUIRE((long long)B * F <= 0x7fffffffLL, BABE_EUNSUPPORTED, "spec_dist_grad: B*F too large");
+  const int rows = B * F;
+  const int grid = std::min((rows + SPEC_THREADS / 32 - 1) / (SPEC_THREADS / 32), sm_count() * 8);
   const float2* x = reinterpret_cast<const float2*>(X);
   const float2* y = reinterpret_cast<const float2*>(Xref);
   float2* gx = reinterpret_cast<float2*>(gX);
   float2* gy = reinterpret_cast<float2*>(gXref);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode == 0) k_spec_dist_grad<0><<<grid, 256, 0, st>>>(x, y, w, coef, F, frames, n, gx, gy);
-  else k_spec_dist_grad<2><<<grid, 256, 0, st>>>(x, y, w, coef, F, frames, n, gx, gy);
+  if (mode == 0) k_spec_dist_grad<0><<<grid, SPEC_THREADS, 0, st>>>(x, y, w, coef, F, frames, rows, gx, gy);
+  else k_spec_dist_grad<2><<<grid, SPEC_THREADS, 0, st>>>(x, y, w, coef, F, frames, rows, gx, gy);
   return check_launch("k_spec_dist_grad");
 }
