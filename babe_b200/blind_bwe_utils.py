@@ -105,6 +105,10 @@ class _FilterIstft(torch.autograd.Function):
         c[0] = 1.0 / nfft
         c[-1] = 1.0 / nfft
         # adjoint of irfft applied to the windowed frames of g / envelope
+        if not ctx.needs_input_grad[1]:
+            # only the spectrogram's gradient is wanted (H fixed, the usual guidance case): H rides in the STFT
+            # kernel's per-bin scale, no separate pass over the spectrogram
+            return ops.stft(g.contiguous(), nfft, frames=M, in_env_div=True, bin_scale=c * H), None, None
         Gs = ops.stft(g.contiguous(), nfft, frames=M, in_env_div=True, bin_scale=c)
         gX = gH = None
         if ctx.needs_input_grad[0]:

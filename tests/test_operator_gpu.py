@@ -185,6 +185,10 @@ def test_stft_istft_stats_vs_oracle(bu, sf, nfft):
     # irfft ignores Im of DC/Nyquist; the oracle's autograd agrees
     assert rel_l2(gcX.cpu(), goX) < TOL
     assert rel_l2(gcH.cpu(), goH) < 5e-5
+    # H fixed (the guidance case): its response rides in the STFT kernel's per-bin scale
+    Xc2 = Xo.cuda().requires_grad_(True)
+    (gcX2,) = torch.autograd.grad((bu.apply_filter_istft(Xc2, H.cuda(), nfft) * cot.cuda()).sum(), Xc2)
+    assert rel_l2(gcX2.cpu(), goX) < TOL
 
 
 def test_fit_params_vs_oracle(golden):
