@@ -502,6 +502,14 @@ def operator_probe(device, peak, fp32_peak):
         "cqt_synthesis_B64": (lambda: cq.bwd(coefs[0]), cqb, op_flops("cqt_synthesis", 64, 0, cq)),
         "hpf_DC_B64": (lambda: cq.apply_hpf_DC(xc), 64 * 8 * AUDIO_LEN, op_flops("hpf", 64, 0, cq)),
     }
+    # a9 / a10: the STFT-distance guidance norm and its gradient on the spectrograms of 64 x 184184 (2049 bins x 88 frames)
+    Xs = torch.randn(64, NFFT // 2 + 1, AUDIO_LEN // (NFFT // 2) - 1, 2, device=device)
+    Rs = torch.randn_like(Xs)
+    wl = torch.linspace(0, 1, NFFT // 2 + 1, device=device)
+    c1 = torch.ones(1, device=device)
+    cases["stft_distance_B64 (value, both spectrograms read)"] = (lambda: ops.spec_dist_stats(Xs, Rs, wl, 0), 8 * Xs.numel(), 0)
+    cases["stft_distance_grad_B64 (both read, one gradient written)"] = (
+        lambda: ops.spec_dist_grad(Xs, Rs, wl, c1, 0), 12 * Xs.numel(), 0)
     Hd = ops.design_filter(fc, A, f, strict=False)
     x8, y8 = x[:8, :AUDIO_LEN // 2].contiguous(), y[:8, :AUDIO_LEN // 2].contiguous()
     p0 = torch.tensor([[280.0, 285, 290, 295, 300], [-15.0, -17, -20, -25, -30]], device=device)
