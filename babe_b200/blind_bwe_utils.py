@@ -114,7 +114,7 @@ class _FilterIstft(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gX = Gs * H[None, :, None, None]
         if ctx.needs_input_grad[1]:
-            gH = (X * Gs).sum(dim=(0, 2, 3))
+            gH = ops.spec_dist_stats(X, Gs, None, mode=3).to(torch.float32)      # per-bin sum of Re(conj(X) G)
         return gX, gH, None
 
 

@@ -937,7 +937,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spec_mag_grad(const float2* X,
 // the plain magnitude distance is k_spec_mag_stats / k_spec_mag_grad with H = 1): one pass over both spectrograms
 // instead of the reference's multiply / subtract / norm chain.  MODE 0: s_k = sum |w X - w Xref|^2,
 // MODE 2: s_k = sum (log10(w|X| + 1e-8) - log10(w|Xref| + 1e-8))^2; fp32 in the reference's operation order,
-// accumulated in double.
+// accumulated in double.  MODE 3: s_k = sum Re(conj(X) Xref), the per-bin correlation that is dL/dH of
+// apply_filter_istft (utils/blind_bwe_utils.py:28-39) when Xref holds the adjoint spectrogram.
 // ---------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(SPEC_THREADS) k_spec_dist_stats(const float2* X, const float2* Xref, const float* w,
@@ -968,6 +969,8 @@ __global__ void __launch_bounds__(SPEC_THREADS) k_spec_dist_stats(const float2* 
         const float dr = __fsub_rn(__fmul_rn(x[u].x, wk), __fmul_rn(y[u].x, wk));
         const float di = __fsub_rn(__fmul_rn(x[u].y, wk), __fmul_rn(y[u].y, wk));
         part = fmaf(dr, dr, fmaf(di, di, part));
+      } else if (MODE == 3) {
+        part = fmaf(x[u].x, y[u].x, fmaf(x[u].y, y[u].y, part));
       } else {
         const float mx = sqrtf(__fadd_rn(__fmul_rn(x[u].x, x[u].x), __fmul_rn(x[u].y, x[u].y)));
         const float my = sqrtf(__fadd_rn(__fmul_rn(y[u].x, y[u].x), __fmul_rn(y[u].y, y[u].y)));
@@ -1131,11 +1134,13 @@ extern "C" int babe_spec_dist_stats(const float* X, const float* Xref, const flo
                                     int frames, double* out, void* stream) {
   BABE_REQUIRE(X && Xref && out, BABE_EBADARG, "spec_dist_stats: null pointer");
   BABE_REQUIRE(B >= 1 && F >= 1 && frames >= 1, BABE_EBADARG, "spec_dist_stats: bad shape");
-  BABE_REQUIRE(mode == 0 || mode == 2, BABE_EBADARG, "spec_dist_stats: mode=%d (0 complex, 2 log-magnitude)", mode);
+  BABE_REQUIRE(mode == 0 || mode == 2 || mode == 3, BABE_EBADARG,
+               "spec_dist_stats: mode=%d (0 complex, 2 log-magnitude, 3 correlation)", mode);
   const float2* x = reinterpret_cast<const float2*>(X);
   const float2* y = reinterpret_cast<const float2*>(Xref);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == 0) k_spec_dist_stats<0><<<F, SPEC_THREADS, 0, st>>>(x, y, w, B, F, frames, out);
+  else if (mode == 3) k_spec_dist_stats<3><<<F, SPEC_THREADS, 0, st>>>(x, y, w, B, F, frames, out);
   else k_spec_dist_stats<2><<<F, SPEC_THREADS, 0, st>>>(x, y, w, B, F, frames, out);
   return check_launch("k_spec_dist_stats");
 }

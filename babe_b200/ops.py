@@ -222,7 +222,8 @@ def spec_mag_grad(X, Xref, H, w, coef, want_X=True, want_Xref=False):
 
 
 def spec_dist_stats(X, Xref, w=None, mode=0):
-    """float64[F] per-bin sums of squares of the complex (mode 0) / log-magnitude (mode 2) spectrogram distance."""
+    """float64[F] per-bin sums of squares of the complex (mode 0) / log-magnitude (mode 2) spectrogram distance;
+    mode 3: per-bin sum of Re(conj(X) Xref)."""
     X = _cuda_f32(X, "X")
     Xref = _cuda_f32(Xref, "Xref")
     if X.shape != Xref.shape or X.dim() != 4 or X.shape[-1] != 2:

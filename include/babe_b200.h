@@ -171,7 +171,8 @@ int babe_spec_mag_grad(const float* X, const float* Xref, const float* H, const 
  * || w X - w Xref ||_2 over re/im) and apply_norm_STFTmag_fweighted(..., logmag=True) (:198-248, mode 2:
  * || log10(w|X| + 1e-8) - log10(w|Xref| + 1e-8) ||_2) from spectrograms [B,F,frames,2]; out is double[F], the per-bin
  * sums of squares (norm = sqrt of their sum).  The plain magnitude distance (:198-248, logmag=False) is
- * babe_spec_mag_stats with H = NULL.  w may be NULL (= 1). */
+ * babe_spec_mag_stats with H = NULL.  w may be NULL (= 1).  mode 3: out[k] = sum_{b,t} Re(conj(X) Xref) (w unused),
+ * the gradient of apply_filter_istft (utils/blind_bwe_utils.py:28-39) wrt H when Xref is the adjoint spectrogram. */
 int babe_spec_dist_stats(const float* X, const float* Xref, const float* w, int mode, int B, int F, int frames,
                          double* out, void* stream);
 /* Gradients of those norms wrt the spectrograms; coef is a 1-element DEVICE array (upstream gradient / norm);
